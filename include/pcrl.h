@@ -1,0 +1,208 @@
+/*
+ * pcrl.h -- C ABI of libpcrl.so: hand-written sm_100a kernels for pyrl's PointNet SAC/DrQ update path.
+ *
+ * The reference (lz1oceani/pointcloud_rl, `pyrl`) is pure Python/PyTorch and has no FFI of its own
+ * (SURVEY.md section 8b); its extension point is the Python registry.  This header is therefore the
+ * boundary the host-side mirror (`pointcloud_rl_b200/`) binds with ctypes.  Every entry point names
+ * the reference code whose arithmetic it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, no host syncs, no
+ *     allocation inside, CUDA-graph capturable
+ *   - return value: 0 = ok, otherwise a PCRL_E* code; pcrl_last_error() gives a message
+ *   - row-major fp32 everywhere unless stated otherwise
+ *   - R = clouds (batch rows after augmentation), N = points per cloud, NP = N rounded up to a
+ *     multiple of 128 (padding points are zero and never win the max-pool), CP = channels padded to 8 or 16
+ */
+#ifndef PCRL_H_
+#define PCRL_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCRL_OK 0
+#define PCRL_EINVAL 1   /* bad argument / unsupported shape */
+#define PCRL_ECUDA 2    /* a CUDA runtime call or launch failed */
+#define PCRL_EUNSUPPORTED 3
+
+#define PCRL_ABI_VERSION 1
+
+/* augmentation kinds for pcrl_stage_points */
+#define PCRL_AUG_NONE 0
+#define PCRL_AUG_JITTER 1 /* RandomJitterPoints: xyz += U(lo,hi) per coordinate (pcd_aug.py:307-322) */
+#define PCRL_AUG_ROTZ 2   /* GlobalRotScaleTrans, rot only: one z-angle ~U(lo,hi) per cloud (pcd_aug.py:178-215) */
+
+int pcrl_abi_version(void);
+const char* pcrl_last_error(void);
+/* number of SMs of the current device (grid sizing on the host side) */
+int pcrl_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * (1) Staging + augmentation.  Replaces GDict.repeat / repeat_interleave (drq.py:58-63,
+ * array_ops.py:106-121), RandomJitterPoints / GlobalRotScaleTrans (pcd_aug.py) and
+ * PointCloudBase.preprocess (pointnet.py:48-63) with one pass: every source cloud is read once and
+ * `repeat` augmented copies are written, interleaved ([b0a0, b0a1, b1a0, ...]).
+ *
+ * inputs (channel-major, as the replay buffer stores them):
+ *   xyz  f32 [B,3,N];  rgb u8 or f32 [B,3,N] (may be NULL; rgb_is_u8 selects /255);
+ *   pos  u8 [B,n_pos,N] (may be NULL);  seg u8/bool [B,n_seg,N] (may be NULL)
+ * randomness: if `noise` != NULL it is used verbatim (parity mode): JITTER -> f32 [B*repeat,3,N],
+ *   ROTZ -> f32 [B*repeat] angles.  Otherwise Philox4x32-10 keyed by (seed, *counter_dev + stream_id).
+ * outputs:
+ *   xf   f32  [B*repeat, NP, CP]  point-major rows (xyz | rgb/255 | pos | seg | 0 pad)
+ *   xh   bf16 tile images for the tcgen05 path, [B*repeat*NP/128][128x16] (may be NULL), holding
+ *        hi parts of all channels, a constant-1 channel (bias) and the lo parts of xyz
+ * row_stride_select: if >1, only source rows are staged for output rows r with r % row_stride_select
+ *   == 0 of an already-staged buffer -- not used here; see pcrl_gather_rows.
+ * ------------------------------------------------------------------------------------------- */
+int pcrl_stage_points(const float* xyz, const void* rgb, int rgb_is_u8, const uint8_t* pos, int n_pos,
+                      const uint8_t* seg, int n_seg, int B, int N, int repeat, int aug_kind, float aug_lo,
+                      float aug_hi, const float* noise, uint64_t seed, const uint64_t* counter_dev,
+                      uint32_t stream_id, float* xf, void* xh, int CP, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (2) PointNet per-point shared MLP + max-pool.  Replaces ConvMLP (mlp.py:15-94; block_utils.py),
+ * LN1d (nn_layer.py:192-225) and feature.max(-1) (pointnet.py:151):
+ *   h0 = relu(W0 x + b0);  h1 = relu(LN(W1 h0; g1,be1,eps));  h2 = relu(LN(W2 h1; g2,be2,eps))
+ *   pooled[r,c] = max_n h2[r,n,c], argmax[r,c] = smallest n attaining it.
+ * weights: w0 [c1,C] (row stride C), b0 [c1], w1 [c2,c1], g1,be1 [c2], w2 [c3,c2], g2,be2 [c3].
+ *
+ * pcrl_pointnet_fwd_f32: exact-fp32 CUDA-core path (the parity path; argmax bit-exact up to fp32
+ *   summation order).  workspace: pcrl_pointnet_fwd_f32_workspace(...) bytes.
+ * pcrl_pointnet_fwd_bf16: fused tcgen05/TMEM path (bf16 operands, fp32 accumulate and LN statistics),
+ *   reads `xh` tile images and pre-packed weight images (pcrl_pointnet_pack_weights).
+ * outputs: pooled f32 [R,c3], argmax i32 [R,c3] (may be NULL on the bf16 path).
+ * ------------------------------------------------------------------------------------------- */
+/* bytes needed to process `clouds` clouds at a time (the call loops over chunks if given less than R) */
+int64_t pcrl_pointnet_fwd_f32_workspace(int clouds, int NP, int c1, int c2, int c3);
+int pcrl_pointnet_fwd_f32(const float* xf, int R, int N, int NP, int CP, int C, const float* w0, const float* b0,
+                          const float* w1, const float* g1, const float* be1, const float* w2, const float* g2,
+                          const float* be2, int c1, int c2, int c3, float ln_eps, float* pooled, int32_t* argmax,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+
+int64_t pcrl_pointnet_wpack_bytes(int c1, int c2, int c3);
+int pcrl_pointnet_pack_weights(const float* w0, const float* b0, const float* w1, const float* g1, const float* be1,
+                               const float* w2, const float* g2, const float* be2, int C, int c1, int c2, int c3,
+                               int rgb_u8 /* xh holds raw 0..255 rgb: fold 1/255 into w0 */, void* wpack,
+                               void* stream);
+int pcrl_pointnet_fwd_bf16(const void* xh, int R, int N, int NP, const void* wpack, int c1, int c2, int c3,
+                           float ln_eps, uint64_t* pool_keys /* [R,c3] scratch */, float* pooled, int32_t* argmax,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (3) Sparse backward of (2) through the saved argmax (autograd of pointnet.py:151 + ConvMLP).
+ * Only points that won the max for at least one channel with a non-zero pooled value carry
+ * gradient; they are compacted, their forward is recomputed and the dense backward runs on the
+ * compacted set.  Gradients are ACCUMULATED into dw0.. (caller zeroes them).
+ *   capacity = max active points the workspace is sized for (<= R*c3).
+ * ------------------------------------------------------------------------------------------- */
+int64_t pcrl_pointnet_bwd_workspace(int R, int NP, int c1, int c2, int c3, int CP);
+int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, const float* pooled,
+                      const int32_t* argmax, const float* dpooled, const float* w0, const float* b0, const float* w1,
+                      const float* g1, const float* be1, const float* w2, const float* g2, const float* be2, int c1,
+                      int c2, int c3, float ln_eps, float* dw0, float* db0, float* dw1, float* dg1, float* dbe1,
+                      float* dw2, float* dg2, float* dbe2, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (4) Dense layers.  y = act(x W^T + b): nn.Linear (+ReLU) of LinearMLP (mlp.py:85-100) and
+ * PointNet.final_mlp[0] (pointnet.py:110).  x [M,K] with row stride ldx, w [Nout,K], y [M,Nout] row
+ * stride ldy.  relu: 0/1.
+ * pcrl_linear_bwd: given dy [M,Nout] (already masked by the caller's activation) computes
+ *   dw += dy^T x, db += colsum(dy) (skipped when dw / db are NULL), and (if dx != NULL) dx = dy W
+ *   (dx row stride lddx).
+ * ------------------------------------------------------------------------------------------- */
+int pcrl_linear_fwd(const float* x, int ldx, const float* w, const float* b, float* y, int ldy, int M, int K,
+                    int Nout, int relu, void* stream);
+int pcrl_linear_bwd(const float* x, int ldx, const float* w, const float* dy, int lddy, float* dw, float* db,
+                    float* dx, int lddx, int M, int K, int Nout, void* stream);
+/* dy *= (y > 0) in place: ReLU backward on the saved post-activation */
+int pcrl_relu_bwd(float* dy, const float* y, int64_t n, void* stream);
+/* out[m,j] = a[m,j] + b[m,j] for j < width (summing the two Q heads' input gradients) */
+int pcrl_add_cols(const float* a, int lda, const float* b, int ldb, float* out, int ldo, int M, int width,
+                  void* stream);
+
+/* LayerNorm over the last dim of [M,D] (nn.LayerNorm, pointnet.py:110, eps 1e-5): y = (x-mu)*rstd*g + b.
+ * fwd saves xhat [M,D] and rstd [M] for bwd.  bwd: dg += sum dy*xhat, db += sum dy, dx (may alias dy). */
+int pcrl_layernorm_fwd(const float* x, const float* g, const float* b, float* y, int ldy, float* xhat, float* rstd,
+                       int M, int D, float eps, void* stream);
+int pcrl_layernorm_bwd(const float* dy, int lddy, const float* xhat, const float* rstd, const float* g, float* dg,
+                       float* db, float* dx, int M, int D, void* stream);
+
+/* copy columns: dst[m, dst_off + j] = src[m * src_row_step, j]  for j < width (Visuomotor's torch.cat of
+ * feature | robot state | action, visuomotor.py:130-144; src_row_step = repeat_interleave / first-aug slicing) */
+int pcrl_copy_cols(const float* src, int lds, int src_row_div, int src_row_mul, float* dst, int ldd, int dst_off,
+                   int M, int width, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (5) Policy head.  TanhGaussianHead 'max-entropy' (gaussian.py:23-50,83-87; distributions.py:45-127):
+ *   mu,ls = chunk(out,2); std = exp(clamp(ls,lo,hi)); u = mu + std*eps; a = tanh(u)*scale+bias;
+ *   neglogp = -sum_j [ logN(u;mu,std) - log(scale*(1-tanh(u)^2)+1e-6) ].
+ * eps: injected [M,A] or NULL -> Philox normal.  eps_out [M,A] always written (needed by bwd).
+ * bwd: given da [M,A] and the scalar g_nlp = dL/dneglogp (same for every row) -> dout [M,2A].
+ * ------------------------------------------------------------------------------------------- */
+int pcrl_tanh_gaussian_fwd(const float* out, int M, int A, float ls_lo, float ls_hi, float scale, float bias,
+                           const float* eps, uint64_t seed, const uint64_t* counter_dev, uint32_t stream_id,
+                           float* action, int ld_action, float* neglogp, float* eps_out, void* stream);
+int pcrl_tanh_gaussian_bwd(const float* out, const float* eps, const float* daction, int ld_daction, float g_nlp,
+                           int M, int A, float ls_lo, float ls_hi, float scale, float* dout, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (6) Targets and losses (sac.py:125-137,182-195; drq.py:75-90).  `scalars` is a device array of
+ * PCRL_NUM_SCALARS floats that receives everything update_parameters() logs; one D2H copy per update.
+ *   alpha_dev: device float holding the cached python float `self.alpha`.
+ * ------------------------------------------------------------------------------------------- */
+#define PCRL_S_CRITIC_LOSS 0
+#define PCRL_S_MAX_ABS_ERR 1
+#define PCRL_S_Q 2
+#define PCRL_S_Q_TARGET 3
+#define PCRL_S_CRITIC_GRAD_SQ 4
+#define PCRL_S_ACTOR_LOSS 5
+#define PCRL_S_ALPHA_LOSS 6
+#define PCRL_S_ENTROPY 7
+#define PCRL_S_ACTOR_GRAD_SQ 8
+#define PCRL_S_ALPHA 9
+#define PCRL_S_ALPHA_GRAD 10
+#define PCRL_NUM_SCALARS 16
+
+/* y[r] = r*reward_scale + (1-done)*gamma*(min(q0,q1) + alpha*neglogp); then mean over each group of
+ * `group` consecutive rows, broadcast back (DrQ, drq.py:84-87; group=1 for SAC).  qt [R,2] row-major. */
+int pcrl_td_target(const float* qt, const float* neglogp, const float* rewards, const uint8_t* dones, int B,
+                   int group, float gamma, float reward_scale, int ignore_dones, const float* alpha_dev, float* y,
+                   void* stream);
+/* critic loss = mse(q, y)*2 over q [R,2]; writes dq [R,2] and scalars 0..3 */
+int pcrl_critic_loss(const float* q, const float* y, int R, float* dq, float* scalars, void* stream);
+/* actor loss = -(mean(min_h q) + alpha*mean(neglogp)); alpha loss = exp(log_alpha)*(entropy - target_entropy).
+ * writes dq [M,2] (-1/M routed to the min head), scalars 5..7, *g_nlp_out... (g_nlp = -alpha/M is computed by
+ * the caller from alpha_dev inside pcrl_tanh_gaussian_bwd_dev), and dlog_alpha[0]. */
+int pcrl_actor_loss(const float* q, const float* neglogp, int M, const float* alpha_dev, const float* log_alpha,
+                    float target_entropy, float* dq, float* dlog_alpha, float* scalars, void* stream);
+/* as pcrl_tanh_gaussian_bwd but g_nlp = -(*alpha_dev)/M read on the device */
+int pcrl_tanh_gaussian_bwd_dev(const float* out, const float* eps, const float* daction, int ld_daction,
+                               const float* alpha_dev, int M, int A, float ls_lo, float ls_hi, float scale,
+                               float* dout, void* stream);
+/* alpha_dev[0] = exp(log_alpha[0]); scalars[PCRL_S_ALPHA] = alpha_dev[0]  (sac.py:195) */
+int pcrl_refresh_alpha(const float* log_alpha, float* alpha_dev, float* scalars, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (7) Fused multi-tensor Adam + grad-norm + Polyak over flat buffers.  Replaces torch.optim.Adam.step
+ * built by build_optimizer (optimizer_utils.py:31-64), ExtendedModuleBase.grad_norm
+ * (module_utils.py:40-45) and soft_update (ops.py:60-90).
+ *   step_dev: device int32 step counter, incremented by the kernel (bias correction reads it).
+ *   grad_scale: multiplies every gradient first (1/world_size after an all-reduce(sum)).
+ *   gradsq_out: device float, receives sum(g^2) of the scaled gradients (sqrt on the host).
+ *   polyak: if target != NULL, target[i] = target[i]*(1-tau) + p_new[i]*tau for i in [poly_begin, poly_end)
+ *           of THIS buffer, target indexed from 0.
+ * ------------------------------------------------------------------------------------------- */
+int pcrl_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                   float eps, float grad_scale, int32_t* step_dev, float* gradsq_out, float* target,
+                   int64_t poly_begin, int64_t poly_end, float tau, void* stream);
+int pcrl_polyak(float* target, const float* source, int64_t n, float tau, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCRL_H_ */

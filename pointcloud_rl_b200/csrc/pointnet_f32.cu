@@ -1,0 +1,335 @@
+// Exact-fp32 PointNet per-point MLP on CUDA cores: the parity path of the forward, and the compacted
+// sparse backward through the saved argmax.  Layer by layer over generic kernels (sgemm.cu,
+// rowwise.cu); the fused tensor-core forward is pointnet_tc.cu.
+#include "common.cuh"
+#include "rowwise.cuh"
+
+namespace pcrl {
+
+// max over the N real points of each cloud, ties -> smallest index (torch.max semantics,
+// pointnet.py:151).  h [rows, NP, c3] post-ReLU.  One thread per (cloud, channel): reads are
+// coalesced across channels.
+__global__ void __launch_bounds__(256) maxpool_points_kernel(const float* __restrict__ h, int rows, int N, int NP,
+                                                             int c3, float* __restrict__ pooled,
+                                                             int32_t* __restrict__ argmax) {
+  const int r = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= c3 || r >= rows) return;
+  const float* p = h + (int64_t)r * NP * c3 + c;
+  float best = p[0];
+  int bi = 0;
+  for (int n = 1; n < N; ++n) {
+    float v = p[(int64_t)n * c3];
+    if (v > best) {
+      best = v;
+      bi = n;
+    }
+  }
+  pooled[(int64_t)r * c3 + c] = best;
+  if (argmax) argmax[(int64_t)r * c3 + c] = bi;
+}
+
+// ---- sparse backward helpers -----------------------------------------------------------------
+
+// flag[r*NP + argmax[r,c]] = 1 for every (r,c) that carries gradient: pooled > 0 (ReLU passes) and
+// dpooled != 0.
+__global__ void mark_active_kernel(const float* __restrict__ pooled, const int32_t* __restrict__ argmax,
+                                   const float* __restrict__ dpooled, int R, int NP, int c3,
+                                   int32_t* __restrict__ flag) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)R * c3) return;
+  if (pooled[e] > 0.f && dpooled[e] != 0.f) {
+    int r = (int)(e / c3);
+    flag[(int64_t)r * NP + argmax[e]] = 1;
+  }
+}
+
+// Per-cloud count of flagged points, then an exclusive scan over clouds (single block), then each
+// cloud writes its compacted slots in ascending point order (deterministic layout).
+__global__ void __launch_bounds__(256) count_active_kernel(const int32_t* __restrict__ flag, int NP,
+                                                           int32_t* __restrict__ counts) {
+  const int r = blockIdx.x;
+  int s = 0;
+  for (int n = threadIdx.x; n < NP; n += blockDim.x) s += flag[(int64_t)r * NP + n];
+  __shared__ int red[256];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) counts[r] = red[0];
+}
+
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __restrict__ counts, int R,
+                                                           int32_t* __restrict__ offsets, int32_t* __restrict__ total,
+                                                           int capacity) {
+  // R is a few thousand at most: serial chunks per thread + one block-wide scan
+  __shared__ int part[1024];
+  const int per = (R + 1023) / 1024;
+  const int b0 = threadIdx.x * per, b1 = min(R, b0 + per);
+  int s = 0;
+  for (int i = b0; i < b1; ++i) s += counts[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int i = 0; i < 1024; ++i) {
+      int t = part[i];
+      part[i] = run;
+      run += t;
+    }
+    *total = min(run, capacity);
+  }
+  __syncthreads();
+  int run = part[threadIdx.x];
+  for (int i = b0; i < b1; ++i) {
+    offsets[i] = run;
+    run += counts[i];
+  }
+}
+
+// slot[r*NP+n] = compacted index (or -1); src[a] = r*NP+n.  One block per cloud, ordered by n.
+__global__ void __launch_bounds__(256) assign_slots_kernel(const int32_t* __restrict__ flag,
+                                                           const int32_t* __restrict__ offsets, int NP, int capacity,
+                                                           int32_t* __restrict__ slot, int32_t* __restrict__ src) {
+  const int r = blockIdx.x;
+  __shared__ int warp_tot[8];
+  __shared__ int base;
+  if (threadIdx.x == 0) base = offsets[r];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int n0 = 0; n0 < NP; n0 += 256) {
+    const int n = n0 + threadIdx.x;
+    const int fl = (n < NP) ? flag[(int64_t)r * NP + n] : 0;
+    const unsigned m = __ballot_sync(0xffffffffu, fl != 0);
+    if (lane == 0) warp_tot[warp] = __popc(m);
+    __syncthreads();
+    int pre = 0;
+    for (int w = 0; w < warp; ++w) pre += warp_tot[w];
+    int tot = 0;
+    for (int w = 0; w < 8; ++w) tot += warp_tot[w];
+    if (n < NP) {
+      int a = -1;
+      if (fl) {
+        a = base + pre + __popc(m & ((1u << lane) - 1));
+        if (a < capacity) src[a] = r * NP + n; else a = -1;
+      }
+      slot[(int64_t)r * NP + n] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) base += tot;
+    __syncthreads();
+  }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ x, int CP, const int32_t* __restrict__ src,
+                                   const int* __restrict__ count, float* __restrict__ out) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int a = (int)(e / CP), c = (int)(e % CP);
+  if (a >= *count) return;
+  out[e] = x[(int64_t)src[a] * CP + c];
+}
+
+// dh2[slot(r, argmax[r,c]), c] = dpooled[r,c]  (dh2 zeroed beforehand)
+__global__ void scatter_dpool_kernel(const float* __restrict__ pooled, const int32_t* __restrict__ argmax,
+                                     const float* __restrict__ dpooled, const int32_t* __restrict__ slot, int R, int NP,
+                                     int c3, float* __restrict__ dh2) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)R * c3) return;
+  if (pooled[e] > 0.f && dpooled[e] != 0.f) {
+    int r = (int)(e / c3), c = (int)(e % c3);
+    int a = slot[(int64_t)r * NP + argmax[e]];
+    if (a >= 0) dh2[(int64_t)a * c3 + c] = dpooled[e];
+  }
+}
+
+__global__ void relu_bwd_rows_kernel(float* __restrict__ dy, const float* __restrict__ y, int width,
+                                     const int* __restrict__ count) {
+  int64_t n = (int64_t)(*count) * width;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride)
+    if (!(y[i] > 0.f)) dy[i] = 0.f;
+}
+
+static int gemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias, int relu, float* C, int ldc,
+                   int M, int K, int Nout, const int* m_dev, cudaStream_t st) {
+  // C[M,Nout] = act(A[M,K] W[Nout,K]^T + bias)
+  GemmArgs g{};
+  g.A = A; g.a_si = lda; g.a_sl = 1;
+  g.B = W; g.b_sl = 1; g.b_sj = ldw;
+  g.C = C; g.ldc = ldc;
+  g.M = M; g.N = Nout; g.K = K;
+  g.bias = bias; g.relu = relu; g.split_k = 1; g.m_dev = m_dev;
+  return launch_sgemm(g, st);
+}
+static int gemm_nn(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int K, int Nout,
+                   const int* m_dev, cudaStream_t st) {
+  // C[M,Nout] = A[M,K] W[K,Nout]
+  GemmArgs g{};
+  g.A = A; g.a_si = lda; g.a_sl = 1;
+  g.B = W; g.b_sl = ldw; g.b_sj = 1;
+  g.C = C; g.ldc = ldc;
+  g.M = M; g.N = Nout; g.K = K;
+  g.split_k = 1; g.m_dev = m_dev;
+  return launch_sgemm(g, st);
+}
+static int gemm_tn_acc(const float* A, int lda, const float* Bm, int ldb, float* C, int ldc, int Mrows, int Na, int Nb,
+                       const int* rows_dev, int expected_rows, cudaStream_t st) {
+  // C[Na,Nb] += A[Mrows,Na]^T Bm[Mrows,Nb]   (contraction over rows, split across CTAs)
+  GemmArgs g{};
+  g.A = A; g.a_si = 1; g.a_sl = lda;
+  g.B = Bm; g.b_sl = ldb; g.b_sj = 1;
+  g.C = C; g.ldc = ldc;
+  g.M = Na; g.N = Nb; g.K = Mrows;
+  g.accumulate = 1; g.k_dev = rows_dev;
+  int64_t tiles = cdiv(Na, 64) * cdiv(Nb, 64);
+  g.split_k = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(4 * sm_count(), tiles), cdiv(expected_rows, 128)));
+  return launch_sgemm(g, st);
+}
+
+}  // namespace pcrl
+
+using namespace pcrl;
+
+extern "C" {
+
+int64_t pcrl_pointnet_fwd_f32_workspace(int clouds, int NP, int c1, int c2, int c3) {
+  return (int64_t)clouds * NP * (c1 + c2 + c3) * sizeof(float);
+}
+
+int pcrl_pointnet_fwd_f32(const float* xf, int R, int N, int NP, int CP, int C, const float* w0, const float* b0,
+                          const float* w1, const float* g1, const float* be1, const float* w2, const float* g2,
+                          const float* be2, int c1, int c2, int c3, float ln_eps, float* pooled, int32_t* argmax,
+                          void* workspace, int64_t workspace_bytes, void* stream) {
+  PCRL_CHECK_ARG(xf && w0 && b0 && w1 && g1 && be1 && w2 && g2 && be2 && pooled && workspace);
+  PCRL_CHECK_ARG(R >= 0 && N > 0 && NP >= N && NP % 128 == 0 && C <= CP);
+  cudaStream_t st = as_stream(stream);
+  const int64_t per_cloud = (int64_t)NP * (c1 + c2 + c3) * sizeof(float);
+  const int chunk = (int)std::min<int64_t>(R, workspace_bytes / per_cloud);
+  PCRL_CHECK_ARG(chunk >= 1 || R == 0);
+  for (int r0 = 0; r0 < R; r0 += chunk) {
+    const int rows = std::min(chunk, R - r0);
+    const int P = rows * NP;
+    float* h0 = reinterpret_cast<float*>(workspace);
+    float* h1 = h0 + (int64_t)P * c1;
+    float* h2 = h1 + (int64_t)P * c2;
+    const float* x = xf + (int64_t)r0 * NP * CP;
+    int rc;
+    // h0 = relu(x W0^T + b0)                     (conv0 + ReLU; no norm: ignore_first_ln)
+    if ((rc = gemm_nt(x, CP, w0, C, b0, 1, h0, c1, P, C, c1, nullptr, st))) return rc;
+    // h1 = relu(LN(h0 W1^T))
+    if ((rc = gemm_nt(h0, c1, w1, c1, nullptr, 0, h1, c2, P, c1, c2, nullptr, st))) return rc;
+    if ((rc = launch_ln_rows(h1, c2, g1, be1, h1, c2, nullptr, nullptr, P, c2, ln_eps, 1, nullptr, st))) return rc;
+    // h2 = relu(LN(h1 W2^T))
+    if ((rc = gemm_nt(h1, c2, w2, c2, nullptr, 0, h2, c3, P, c2, c3, nullptr, st))) return rc;
+    if ((rc = launch_ln_rows(h2, c3, g2, be2, h2, c3, nullptr, nullptr, P, c3, ln_eps, 1, nullptr, st))) return rc;
+    dim3 grid((unsigned)cdiv(c3, 256), (unsigned)rows);
+    maxpool_points_kernel<<<grid, 256, 0, st>>>(h2, rows, N, NP, c3, pooled + (int64_t)r0 * c3,
+                                                argmax ? argmax + (int64_t)r0 * c3 : nullptr);
+    PCRL_CHECK_LAUNCH();
+  }
+  return PCRL_OK;
+}
+
+// workspace layout of the backward (A = capacity = R*c3 active points at most)
+struct BwdWs {
+  int32_t *flag, *slot, *src, *counts, *offsets, *total;
+  float *xa, *h0, *y1hat, *rstd1, *h1, *y2hat, *rstd2, *d2, *d1, *d0;
+  int64_t bytes;
+};
+static BwdWs carve_bwd(void* base, int R, int NP, int c1, int c2, int c3, int CP) {
+  BwdWs w{};
+  char* p = reinterpret_cast<char*>(base);
+  const int64_t A = (int64_t)R * c3;
+  auto take = [&](int64_t bytes) {
+    char* q = p;
+    p += align_up(bytes, 256);
+    return q;
+  };
+  w.flag = (int32_t*)take((int64_t)R * NP * 4);
+  w.slot = (int32_t*)take((int64_t)R * NP * 4);
+  w.src = (int32_t*)take(A * 4);
+  w.counts = (int32_t*)take((int64_t)R * 4);
+  w.offsets = (int32_t*)take((int64_t)R * 4);
+  w.total = (int32_t*)take(256);
+  w.xa = (float*)take(A * CP * 4);
+  w.h0 = (float*)take(A * c1 * 4);
+  w.y1hat = (float*)take(A * c2 * 4);
+  w.rstd1 = (float*)take(A * 4);
+  w.h1 = (float*)take(A * c2 * 4);
+  w.y2hat = (float*)take(A * c3 * 4);
+  w.rstd2 = (float*)take(A * 4);
+  w.d2 = (float*)take(A * c3 * 4);
+  w.d1 = (float*)take(A * c2 * 4);
+  w.d0 = (float*)take(A * c1 * 4);
+  w.bytes = p - reinterpret_cast<char*>(base);
+  return w;
+}
+
+int64_t pcrl_pointnet_bwd_workspace(int R, int NP, int c1, int c2, int c3, int CP) {
+  return carve_bwd(nullptr, R, NP, c1, c2, c3, CP).bytes;
+}
+
+int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, const float* pooled,
+                      const int32_t* argmax, const float* dpooled, const float* w0, const float* b0, const float* w1,
+                      const float* g1, const float* be1, const float* w2, const float* g2, const float* be2, int c1,
+                      int c2, int c3, float ln_eps, float* dw0, float* db0, float* dw1, float* dg1, float* dbe1,
+                      float* dw2, float* dg2, float* dbe2, void* workspace, int64_t workspace_bytes, void* stream) {
+  PCRL_CHECK_ARG(xf && pooled && argmax && dpooled && workspace && dw0 && db0 && dw1 && dg1 && dbe1 && dw2 && dg2 && dbe2);
+  PCRL_CHECK_ARG(R >= 0 && NP % 128 == 0 && NP >= N && C <= CP && R <= 1024 * 1024);
+  if (R == 0) return PCRL_OK;
+  cudaStream_t st = as_stream(stream);
+  BwdWs w = carve_bwd(workspace, R, NP, c1, c2, c3, CP);
+  PCRL_CHECK_ARG(w.bytes <= workspace_bytes);
+  const int A = R * c3;  // capacity
+  const int expect = std::max(1, A * 3 / 4);
+  int rc;
+
+  // 1. which points carry gradient; compact them
+  PCRL_CHECK_CUDA(cudaMemsetAsync(w.flag, 0, (int64_t)R * NP * 4, st));
+  mark_active_kernel<<<(unsigned)cdiv((int64_t)R * c3, 256), 256, 0, st>>>(pooled, argmax, dpooled, R, NP, c3, w.flag);
+  PCRL_CHECK_LAUNCH();
+  count_active_kernel<<<R, 256, 0, st>>>(w.flag, NP, w.counts);
+  PCRL_CHECK_LAUNCH();
+  scan_counts_kernel<<<1, 1024, 0, st>>>(w.counts, R, w.offsets, w.total, A);
+  PCRL_CHECK_LAUNCH();
+  assign_slots_kernel<<<R, 256, 0, st>>>(w.flag, w.offsets, NP, A, w.slot, w.src);
+  PCRL_CHECK_LAUNCH();
+  gather_rows_kernel<<<(unsigned)cdiv((int64_t)A * CP, 256), 256, 0, st>>>(xf, CP, w.src, w.total, w.xa);
+  PCRL_CHECK_LAUNCH();
+
+  // 2. recompute the forward of the active points, keeping what LN backward needs
+  if ((rc = gemm_nt(w.xa, CP, w0, C, b0, 1, w.h0, c1, A, C, c1, w.total, st))) return rc;
+  if ((rc = gemm_nt(w.h0, c1, w1, c1, nullptr, 0, w.h1, c2, A, c1, c2, w.total, st))) return rc;
+  if ((rc = launch_ln_rows(w.h1, c2, g1, be1, w.h1, c2, w.y1hat, w.rstd1, A, c2, ln_eps, 1, w.total, st))) return rc;
+  if ((rc = gemm_nt(w.h1, c2, w2, c2, nullptr, 0, w.d2, c3, A, c2, c3, w.total, st))) return rc;
+  // (the post-LN activation of layer 2 itself is not needed: only xhat2 / rstd2)
+  if ((rc = launch_ln_rows(w.d2, c3, g2, be2, w.d2, c3, w.y2hat, w.rstd2, A, c3, ln_eps, 1, w.total, st))) return rc;
+
+  // 3. dL/dh2: zero except the argmax entries (ReLU mask holds there: pooled > 0)
+  PCRL_CHECK_CUDA(cudaMemsetAsync(w.d2, 0, (int64_t)A * c3 * 4, st));
+  scatter_dpool_kernel<<<(unsigned)cdiv((int64_t)R * c3, 256), 256, 0, st>>>(pooled, argmax, dpooled, w.slot, R, NP,
+                                                                              c3, w.d2);
+  PCRL_CHECK_LAUNCH();
+
+  // 4. layer 2 backward: LN -> dW2, dh1
+  if ((rc = launch_ln_rows_bwd(w.d2, c3, w.y2hat, w.rstd2, g2, dg2, dbe2, w.d2, c3, A, c3, w.total, st))) return rc;
+  if ((rc = gemm_tn_acc(w.d2, c3, w.h1, c2, dw2, c2, A, c3, c2, w.total, expect, st))) return rc;
+  if ((rc = gemm_nn(w.d2, c3, w2, c2, w.d1, c2, A, c3, c2, w.total, st))) return rc;
+  relu_bwd_rows_kernel<<<sm_count() * 4, 256, 0, st>>>(w.d1, w.h1, c2, w.total);
+  PCRL_CHECK_LAUNCH();
+  // 5. layer 1 backward
+  if ((rc = launch_ln_rows_bwd(w.d1, c2, w.y1hat, w.rstd1, g1, dg1, dbe1, w.d1, c2, A, c2, w.total, st))) return rc;
+  if ((rc = gemm_tn_acc(w.d1, c2, w.h0, c1, dw1, c1, A, c2, c1, w.total, expect, st))) return rc;
+  if ((rc = gemm_nn(w.d1, c2, w1, c1, w.d0, c1, A, c2, c1, w.total, st))) return rc;
+  relu_bwd_rows_kernel<<<sm_count() * 4, 256, 0, st>>>(w.d0, w.h0, c1, w.total);
+  PCRL_CHECK_LAUNCH();
+  // 6. layer 0 backward: dW0 [c1,C] += d0^T xa[:, :C];  db0 += colsum(d0)
+  if ((rc = gemm_tn_acc(w.d0, c1, w.xa, CP, dw0, C, A, c1, C, w.total, expect, st))) return rc;
+  if ((rc = launch_colsum(w.d0, c1, A, c1, w.total, db0, st))) return rc;
+  return PCRL_OK;
+}
+
+}  // extern "C"

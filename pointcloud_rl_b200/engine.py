@@ -1,0 +1,506 @@
+"""Update engine: device-resident state + kernel sequencing for one SAC / DrQ `update_parameters`.
+
+Mirrors, step for step, pyrl/methods/mfrl/sac.py:103-214 and drq.py:46-165 (ordered spec: SURVEY.md
+Appendix B), but every arithmetic step is a libpcrl kernel launched through the C ABI
+(include/pcrl.h).  PyTorch is used for device memory, streams and (dist.py) NCCL only -- there is no
+autograd and no torch math on this path, and no CPU fallback.
+
+Redundant work the reference does is removed without changing the maths: the 6 PointNet forwards per
+update collapse to the 3 distinct ones (next_obs, obs with grad, first-aug obs with post-step weights),
+and the two Q heads' feature gradients are summed before the single PointNet backward.
+"""
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from ._lib import lib, stream_ptr
+
+S_NAMES = [
+    "critic_loss", "max_critic_abs_err", "q", "q_target", "critic_grad_sq", "actor_loss", "alpha_loss",
+    "entropy", "actor_grad_sq", "alpha", "alpha_grad",
+]
+NUM_SCALARS = 16
+AUG_KINDS = {None: 0, "none": 0, "jitter": 1, "rot": 2}
+MLP_KEYS = ["w0", "b0", "w1", "b1", "w2", "b2"]
+PN_KEYS = ["pn.w0", "pn.b0", "pn.w1", "pn.g1", "pn.be1", "pn.w2", "pn.g2", "pn.be2", "pn.wf", "pn.bf", "pn.gf", "pn.bef"]
+
+
+def _align(n, a):
+    return (n + a - 1) // a * a
+
+
+@dataclass
+class PathSpec:
+    """Shapes of the path (B, N, C, c=(c1,c2,c3), D, S, A)."""
+
+    n_points: int
+    action_dim: int
+    state_dim: int = 0
+    has_rgb: bool = True
+    rgb_u8: bool = True
+    n_pos: int = 0
+    n_seg: int = 0
+    widths: Tuple[int, int, int] = (128, 128, 256)
+    out_dim: int = 128
+    hidden: Tuple[int, int] = (1024, 1024)
+    ln_eps: float = 1e-6
+    head_ln_eps: float = 1e-5
+
+    @property
+    def C(self):
+        return 3 + (3 if self.has_rgb else 0) + self.n_pos + self.n_seg
+
+    @property
+    def CP(self):
+        return 8 if self.C <= 8 else 16
+
+    @property
+    def NP(self):
+        return _align(self.n_points, 128)
+
+    def param_shapes(self):
+        c1, c2, c3 = self.widths
+        D, S, A = self.out_dim, self.state_dim, self.action_dim
+        h1, h2 = self.hidden
+        pn = {
+            "pn.w0": (c1, self.C), "pn.b0": (c1,), "pn.w1": (c2, c1), "pn.g1": (c2,), "pn.be1": (c2,),
+            "pn.w2": (c3, c2), "pn.g2": (c3,), "pn.be2": (c3,), "pn.wf": (D, c3), "pn.bf": (D,), "pn.gf": (D,),
+            "pn.bef": (D,),
+        }
+
+        def mlp(net, din, dout):
+            return {
+                f"{net}.w0": (h1, din), f"{net}.b0": (h1,), f"{net}.w1": (h2, h1), f"{net}.b1": (h2,),
+                f"{net}.w2": (dout, h2), f"{net}.b2": (dout,),
+            }
+
+        groups = {
+            "critic": {**pn, **mlp("q0", D + S + A, 1), **mlp("q1", D + S + A, 1)},
+            "actor": mlp("actor", D + S, 2 * A),
+            "alpha": {"log_alpha": (1,)},
+            "target": {**mlp("tq0", D + S + A, 1), **mlp("tq1", D + S + A, 1)},
+        }
+        return groups
+
+
+@dataclass
+class HyperParams:
+    algo: str = "sac"
+    gamma: float = 0.99
+    reward_scale: float = 1.0
+    num_aug: int = 1
+    aug: Optional[str] = None
+    aug_lo: float = 0.0
+    aug_hi: float = 0.0
+    tau: float = 0.01
+    actor_update_interval: int = 2
+    target_update_interval: int = 2
+    lr: float = 1e-3
+    actor_lr: float = 1e-3
+    alpha_lr: float = 1e-3
+    betas: Tuple[float, float] = (0.9, 0.999)
+    alpha_betas: Tuple[float, float] = (0.5, 0.999)
+    adam_eps: float = 1e-8
+    log_std_bound: Tuple[float, float] = (-10.0, 2.0)
+    head_scale: float = 1.0
+    head_bias: float = 0.0
+    target_entropy: Optional[float] = None
+    ignore_dones: bool = False
+    automatic_alpha_tuning: bool = True
+
+
+class ParamLayout:
+    """One flat fp32 buffer [critic | actor | alpha | target]; every tensor 16-byte aligned so the fused
+    Adam / Polyak kernels run float4-wide over whole groups."""
+
+    def __init__(self, spec: PathSpec):
+        self.entries: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
+        self.group_range: Dict[str, Tuple[int, int]] = {}
+        off = 0
+        for gname, tensors in spec.param_shapes().items():
+            g0 = off
+            for name, shape in tensors.items():
+                self.entries[name] = (off, shape)
+                off += _align(int(np.prod(shape)), 4)
+            self.group_range[gname] = (g0, off)
+        self.total = off
+        self.trainable = self.group_range["alpha"][1]  # critic | actor | alpha carry grads + Adam state
+        c0 = self.group_range["critic"][0]
+        self.q_range = (self.entries["q0.w0"][0] - c0, self.group_range["critic"][1] - c0)  # inside critic group
+        assert self.q_range[1] - self.q_range[0] == self.group_range["target"][1] - self.group_range["target"][0]
+
+    def views(self, flat: torch.Tensor, names=None):
+        out = {}
+        for name, (off, shape) in self.entries.items():
+            if off + int(np.prod(shape)) > flat.numel():
+                continue
+            if names is None or name in names:
+                out[name] = flat[off: off + int(np.prod(shape))].view(*shape)
+        return out
+
+
+class UpdateEngine:
+    def __init__(self, spec: PathSpec, hp: HyperParams, batch_size: int, device="cuda:0", precision="fp32",
+                 seed: int = 0, fwd_chunk_clouds: int = 64):
+        assert precision in ("fp32", "bf16")
+        self.L = lib()
+        self.spec, self.hp, self.B = spec, hp, int(batch_size)
+        self.k = hp.num_aug if hp.algo == "drq" else 1
+        self.R = self.B * self.k
+        self.device = torch.device(device)
+        self.precision = precision
+        self.seed = int(seed)
+        self.layout = ParamLayout(spec)
+        dev = self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.params = torch.zeros(self.layout.total, **f32)
+        self.grads = torch.zeros(self.layout.trainable, **f32)
+        self.adam_m = torch.zeros(self.layout.trainable, **f32)
+        self.adam_v = torch.zeros(self.layout.trainable, **f32)
+        self.p = self.layout.views(self.params)
+        self.g = self.layout.views(self.grads)
+        self.steps = torch.zeros(4, dtype=torch.int32, device=dev)  # critic, actor, alpha Adam step counters
+        self.alpha_dev = torch.zeros(1, **f32)
+        self.scalars = torch.zeros(NUM_SCALARS, **f32)
+        self.scalars_host = torch.zeros(NUM_SCALARS, dtype=torch.float32).pin_memory() if dev.type == "cuda" else None
+        self.counter = torch.zeros(1, dtype=torch.int64, device=dev)  # Philox offset, bumped every update
+        self.world_size = 1
+        self.allreduce = None  # set by dist.attach(): callable(flat_grad_view)
+        self._alloc_workspace(fwd_chunk_clouds)
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc_workspace(self, fwd_chunk_clouds):
+        sp, B, R, dev = self.spec, self.B, self.R, self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        N, NP, CP, A, S, D = sp.n_points, sp.NP, sp.CP, sp.action_dim, sp.state_dim, sp.out_dim
+        c1, c2, c3 = sp.widths
+        h1, h2 = sp.hidden
+        u8 = dict(dtype=torch.uint8, device=dev)
+        self.raw = {}
+        for which in ("obs", "next_obs"):
+            d = {"xyz": torch.zeros(B, 3, N, **f32)}
+            if sp.has_rgb:
+                d["rgb"] = torch.zeros(B, 3, N, **(u8 if sp.rgb_u8 else f32))
+            if sp.n_pos:
+                d["pos_encoding"] = torch.zeros(B, sp.n_pos, N, **u8)
+            if sp.n_seg:
+                d["seg"] = torch.zeros(B, sp.n_seg, N, **u8)
+            if S:
+                d["state"] = torch.zeros(B, S, **f32)
+            self.raw[which] = d
+        self.raw["actions"] = torch.zeros(B, A, **f32)
+        self.raw["rewards"] = torch.zeros(B, **f32)
+        self.raw["dones"] = torch.zeros(B, **u8)
+        self._pinned = None
+
+        w = {}
+        bf16 = self.precision == "bf16"
+        for name, rows in (("next", R), ("obs", R), ("pi", B)):
+            w[f"xf_{name}"] = torch.zeros(rows, NP, CP, **f32)
+            if bf16:
+                w[f"xh_{name}"] = torch.zeros(rows * NP * 16, dtype=torch.bfloat16, device=dev)
+            w[f"pooled_{name}"] = torch.zeros(rows, c3, **f32)
+            w[f"cat_{name}"] = torch.zeros(rows, D + S + A, **f32)
+            w[f"z_{name}"] = torch.zeros(rows, D, **f32)
+            w[f"nlp_{name}"] = torch.zeros(rows, **f32)
+            w[f"eps_{name}"] = torch.zeros(rows, A, **f32)
+            w[f"out_{name}"] = torch.zeros(rows, 2 * A, **f32)
+            w[f"q_{name}"] = torch.zeros(rows, 2, **f32)
+        w["argmax_obs"] = torch.zeros(R, c3, dtype=torch.int32, device=dev)
+        w["xhat_obs"] = torch.zeros(R, D, **f32)
+        w["rstd_obs"] = torch.zeros(R, **f32)
+        w["y"] = torch.zeros(R, **f32)
+        w["dq"] = torch.zeros(R, 2, **f32)
+        w["dz"] = torch.zeros(R, D, **f32)
+        w["dpooled"] = torch.zeros(R, c3, **f32)
+        w["dout"] = torch.zeros(B, 2 * A, **f32)
+        w["dlog_alpha"] = self.g["log_alpha"]
+        # MLP activations: [net][layer]; no-grad passes reuse "tmp"
+        for net in ("tmp", "q0", "q1", "actor"):
+            w[f"h1_{net}"] = torch.zeros(R, h1, **f32)
+            w[f"h2_{net}"] = torch.zeros(R, h2, **f32)
+        w["dh1"] = torch.zeros(R, h1, **f32)
+        w["dh2"] = torch.zeros(R, h2, **f32)
+        w["dx0"] = torch.zeros(R, D + S + A, **f32)
+        w["dx1"] = torch.zeros(R, D + S + A, **f32)
+        chunk = max(1, min(R, fwd_chunk_clouds))
+        self.fwd_ws_bytes = int(self.L.pointnet_fwd_f32_workspace(chunk, NP, c1, c2, c3))
+        self.bwd_ws_bytes = int(self.L.pointnet_bwd_workspace(R, NP, c1, c2, c3, CP))
+        w["scratch"] = torch.zeros(max(self.fwd_ws_bytes, self.bwd_ws_bytes), dtype=torch.uint8, device=dev)
+        if bf16:
+            w["wpack"] = torch.zeros(int(self.L.pointnet_wpack_bytes(c1, c2, c3)), dtype=torch.uint8, device=dev)
+            w["pool_keys"] = torch.zeros(R * c3, dtype=torch.int64, device=dev)
+        self.w = w
+        self._wpack_dirty = True
+
+    # ------------------------------------------------------------------ parameters
+    def load_params(self, params: Dict[str, torch.Tensor]):
+        """Copies oracle/reference-named tensors (pn.*, actor.*, q0.*, q1.*, [tq0.*, tq1.*], log_alpha)."""
+        for name, view in self.p.items():
+            src = params.get(name)
+            if src is None and name.startswith("tq"):
+                src = params[name[1:]]  # hard_update(target, critic), builder.py:43
+            if src is None:
+                raise KeyError(f"missing parameter {name}")
+            view.copy_(torch.as_tensor(src, dtype=torch.float32).reshape(view.shape))
+        self.refresh_alpha()
+        self._wpack_dirty = True
+
+    def export_params(self):
+        return {k: v.detach().clone().cpu() for k, v in self.p.items()}
+
+    def refresh_alpha(self):
+        self.L.refresh_alpha(self.p["log_alpha"], self.alpha_dev, self.scalars, stream_ptr())
+
+    # ------------------------------------------------------------------ batch upload (host -> device)
+    def upload_batch(self, batch):
+        """batch: dict(obs, next_obs, actions, rewards, dones) of numpy arrays / torch CPU tensors (the
+        reference's `memory.sample(B)` layout, replay_buffer.py:297-322).  Host->device copies go through
+        pinned staging buffers so they are asynchronous on the current stream."""
+        flat = self._flatten_batch(batch)
+        nbytes = 0
+        if self._pinned is None:
+            self._pinned = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in flat.items()}
+        for key, src in flat.items():
+            dst = self._device_leaf(key)
+            pin = self._pinned[key]
+            pin.copy_(src)
+            dst.copy_(pin, non_blocking=True)
+            nbytes += pin.numel() * pin.element_size()
+        return nbytes
+
+    def _device_leaf(self, key):
+        if "/" in key:
+            a, b = key.split("/")
+            return self.raw[a][b]
+        return self.raw[key]
+
+    def _flatten_batch(self, batch):
+        out = {}
+        for which in ("obs", "next_obs"):
+            obs = batch[which]
+            for k, v in obs.items():
+                kk = "state" if k in ("state", "agent") else k
+                if kk not in self.raw[which]:
+                    continue
+                t = torch.as_tensor(np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v)
+                tgt = self.raw[which][kk]
+                if t.dtype == torch.bool:
+                    t = t.to(torch.uint8)
+                out[f"{which}/{kk}"] = t.to(tgt.dtype).reshape(tgt.shape)
+        out["actions"] = torch.as_tensor(batch["actions"]).float().reshape(self.B, -1)
+        out["rewards"] = torch.as_tensor(batch["rewards"]).float().reshape(self.B)
+        out["dones"] = torch.as_tensor(np.asarray(batch["dones"]).astype(np.uint8)).reshape(self.B)
+        return out
+
+    # ------------------------------------------------------------------ building blocks
+    def _stage(self, which, name, repeat, aug_kind, noise, stream_id, st):
+        sp, raw = self.spec, self.raw[which]
+        self.L.stage_points(
+            raw["xyz"], raw.get("rgb"), int(sp.rgb_u8), raw.get("pos_encoding"), sp.n_pos, raw.get("seg"), sp.n_seg,
+            self.B, sp.n_points, repeat, aug_kind, float(self.hp.aug_lo), float(self.hp.aug_hi), noise, self.seed,
+            self.counter, stream_id, self.w[f"xf_{name}"], self.w.get(f"xh_{name}"), sp.CP, st)
+
+    def _encode(self, name, rows, want_argmax, st):
+        """PointNet per-point MLP + max-pool (pointnet.py:147-151) then final_mlp (pointnet.py:110,152-153):
+        writes the feature into cat_<name>[:, :D]."""
+        sp, w, p = self.spec, self.w, self.p
+        c1, c2, c3 = sp.widths
+        argmax = w["argmax_obs"] if want_argmax else None
+        if self.precision == "bf16":
+            if self._wpack_dirty:
+                self.L.pointnet_pack_weights(p["pn.w0"], p["pn.b0"], p["pn.w1"], p["pn.g1"], p["pn.be1"], p["pn.w2"],
+                                             p["pn.g2"], p["pn.be2"], sp.C, c1, c2, c3,
+                                             int(sp.has_rgb and sp.rgb_u8), w["wpack"], st)
+                self._wpack_dirty = False
+            self.L.pointnet_fwd_bf16(w[f"xh_{name}"], rows, sp.n_points, sp.NP, w["wpack"], c1, c2, c3, sp.ln_eps,
+                                     w["pool_keys"], w[f"pooled_{name}"], argmax, st)
+        else:
+            self.L.pointnet_fwd_f32(w[f"xf_{name}"], rows, sp.n_points, sp.NP, sp.CP, sp.C, p["pn.w0"], p["pn.b0"],
+                                    p["pn.w1"], p["pn.g1"], p["pn.be1"], p["pn.w2"], p["pn.g2"], p["pn.be2"], c1, c2,
+                                    c3, sp.ln_eps, w[f"pooled_{name}"], argmax, w["scratch"], self.fwd_ws_bytes, st)
+        D = sp.out_dim
+        cat = w[f"cat_{name}"]
+        self.L.linear_fwd(w[f"pooled_{name}"], c3, p["pn.wf"], p["pn.bf"], w[f"z_{name}"], D, rows, c3, D, 0, st)
+        save = want_argmax
+        self.L.layernorm_fwd(w[f"z_{name}"], p["pn.gf"], p["pn.bef"], cat, cat.stride(0),
+                             w["xhat_obs"] if save else None, w["rstd_obs"] if save else None, rows, D,
+                             sp.head_ln_eps, st)
+
+    def _mlp_fwd(self, net, x, K, M, out, ldo, nout, keep, st):
+        p, (h1n, h2n) = self.p, self.spec.hidden
+        h1, h2 = self.w[f"h1_{keep}"], self.w[f"h2_{keep}"]
+        ldx = x.stride(0)
+        self.L.linear_fwd(x, ldx, p[f"{net}.w0"], p[f"{net}.b0"], h1, h1n, M, K, h1n, 1, st)
+        self.L.linear_fwd(h1, h1n, p[f"{net}.w1"], p[f"{net}.b1"], h2, h2n, M, h1n, h2n, 1, st)
+        self.L.linear_fwd(h2, h2n, p[f"{net}.w2"], p[f"{net}.b2"], out, ldo, M, h2n, nout, 0, st)
+
+    def _mlp_bwd(self, net, x, K, M, dout, lddo, nout, keep, dx, want_w, st):
+        p, g, w, (h1n, h2n) = self.p, self.g, self.w, self.spec.hidden
+        h1, h2 = w[f"h1_{keep}"], w[f"h2_{keep}"]
+        gw = (lambda n: g[f"{net}.{n}"]) if want_w else (lambda n: None)
+        self.L.linear_bwd(h2, h2n, p[f"{net}.w2"], dout, lddo, gw("w2"), gw("b2"), w["dh2"], h2n, M, h2n, nout, st)
+        self.L.relu_bwd(w["dh2"], h2, M * h2n, st)
+        self.L.linear_bwd(h1, h1n, p[f"{net}.w1"], w["dh2"], h2n, gw("w1"), gw("b1"), w["dh1"], h1n, M, h1n, h2n, st)
+        self.L.relu_bwd(w["dh1"], h1, M * h1n, st)
+        self.L.linear_bwd(x, x.stride(0), p[f"{net}.w0"], w["dh1"], h1n, gw("w0"), gw("b0"), dx,
+                          dx.stride(0) if dx is not None else 0, M, K, h1n, st)
+
+    def _adam(self, group, idx, lr, betas, gradsq_slot, polyak, st):
+        lo, hi = self.layout.group_range[group]
+        hp = self.hp
+        target, pb, pe = None, 0, 0
+        if polyak:
+            t0, t1 = self.layout.group_range["target"]
+            target = self.params[t0:t1]
+            pb, pe = self.layout.q_range
+        self.L.adam_step(self.params[lo:hi], self.grads[lo:hi], self.adam_m[lo:hi], self.adam_v[lo:hi], hi - lo,
+                         float(lr), float(betas[0]), float(betas[1]), float(hp.adam_eps), 1.0 / self.world_size,
+                         self.steps[idx:], self.scalars[gradsq_slot:] if gradsq_slot is not None else None, target,
+                         pb, pe, float(hp.tau), st)
+
+    # ------------------------------------------------------------------ the update
+    def update(self, updates: int, noise: Optional[Dict[str, torch.Tensor]] = None):
+        """Enqueues one full update on the current stream.  `noise` (parity mode) injects the reference's
+        random draws: jitter_obs/jitter_next or angle_obs/angle_next, eps_next, eps_pi (device tensors)."""
+        sp, hp, w, p, L = self.spec, self.hp, self.w, self.p, self.L
+        st = stream_ptr()
+        B, R, k = self.B, self.R, self.k
+        D, S, A = sp.out_dim, sp.state_dim, sp.action_dim
+        c1, c2, c3 = sp.widths
+        noise = noise or {}
+        aug = AUG_KINDS[hp.aug] if hp.algo == "drq" else 0
+        nkey = {1: "jitter", 2: "angle"}.get(aug)
+        do_actor = updates % hp.actor_update_interval == 0
+        do_target = updates % hp.target_update_interval == 0
+        ld_cat = D + S + A
+        target_entropy = float(hp.target_entropy) if hp.target_entropy is not None else -float(A)
+
+        # ---- staging (+ augmentation fused into the load)
+        self._stage("next_obs", "next", k, aug, noise.get(f"{nkey}_next") if nkey else None, 1, st)
+        self._stage("obs", "obs", k, aug, noise.get(f"{nkey}_obs") if nkey else None, 0, st)
+
+        # ---- TD target (no grad): sac.py:108-134 / drq.py:71-87
+        self._encode("next", R, False, st)
+        cat = w["cat_next"]
+        if S:
+            L.copy_cols(self.raw["next_obs"]["state"], S, k, 1, cat, ld_cat, D, R, S, st)
+        self._mlp_fwd("actor", cat, D + S, R, w["out_next"], 2 * A, 2 * A, "tmp", st)
+        L.tanh_gaussian_fwd(w["out_next"], R, A, hp.log_std_bound[0], hp.log_std_bound[1], hp.head_scale, hp.head_bias,
+                            noise.get("eps_next"), self.seed, self.counter, 2, cat[:, D + S:], ld_cat, w["nlp_next"],
+                            w["eps_next"], st)
+        self._mlp_fwd("tq0", cat, ld_cat, R, w["q_next"], 2, 1, "tmp", st)
+        self._mlp_fwd("tq1", cat, ld_cat, R, w["q_next"][:, 1:], 2, 1, "tmp", st)
+        L.td_target(w["q_next"], w["nlp_next"], self.raw["rewards"], self.raw["dones"], B, k, hp.gamma,
+                    1.0 if hp.algo == "drq" else hp.reward_scale, int(hp.ignore_dones), self.alpha_dev, w["y"], st)
+
+        # ---- critic step: sac.py:136-148 / drq.py:89-101
+        self._encode("obs", R, True, st)
+        cat = w["cat_obs"]
+        if S:
+            L.copy_cols(self.raw["obs"]["state"], S, k, 1, cat, ld_cat, D, R, S, st)
+        L.copy_cols(self.raw["actions"], A, k, 1, cat, ld_cat, D + S, R, A, st)
+        self._mlp_fwd("q0", cat, ld_cat, R, w["q_obs"], 2, 1, "q0", st)
+        self._mlp_fwd("q1", cat, ld_cat, R, w["q_obs"][:, 1:], 2, 1, "q1", st)
+        L.critic_loss(w["q_obs"], w["y"], R, w["dq"], self.scalars, st)
+        c_lo, c_hi = self.layout.group_range["critic"]
+        self.grads[c_lo:c_hi].zero_()
+        self._mlp_bwd("q0", cat, ld_cat, R, w["dq"], 2, 1, "q0", w["dx0"], True, st)
+        self._mlp_bwd("q1", cat, ld_cat, R, w["dq"][:, 1:], 2, 1, "q1", w["dx1"], True, st)
+        L.add_cols(w["dx0"], ld_cat, w["dx1"], ld_cat, w["dz"], D, R, D, st)  # both heads' d/dfeature add up
+        L.layernorm_bwd(w["dz"], D, w["xhat_obs"], w["rstd_obs"], p["pn.gf"], self.g["pn.gf"], self.g["pn.bef"],
+                        w["dz"], R, D, st)
+        L.linear_bwd(w["pooled_obs"], c3, p["pn.wf"], w["dz"], D, self.g["pn.wf"], self.g["pn.bf"], w["dpooled"], c3,
+                     R, c3, D, st)
+        g = self.g
+        L.pointnet_bwd(w["xf_obs"], R, sp.n_points, sp.NP, sp.CP, sp.C, w["pooled_obs"], w["argmax_obs"], w["dpooled"],
+                       p["pn.w0"], p["pn.b0"], p["pn.w1"], p["pn.g1"], p["pn.be1"], p["pn.w2"], p["pn.g2"],
+                       p["pn.be2"], c1, c2, c3, sp.ln_eps, g["pn.w0"], g["pn.b0"], g["pn.w1"], g["pn.g1"], g["pn.be1"],
+                       g["pn.w2"], g["pn.g2"], g["pn.be2"], w["scratch"], self.bwd_ws_bytes, st)
+        if self.allreduce is not None:
+            self.allreduce(self.grads[c_lo:c_hi])
+        self._adam("critic", 0, hp.lr, hp.betas, 4, do_target, st)  # + Polyak fused (sac.py:207-208)
+        self._wpack_dirty = True
+
+        # ---- actor + alpha step: sac.py:161-205 / drq.py:114-155
+        if do_actor:
+            if k > 1:  # first augmentation of every sample (drq.py:115)
+                self._take_first_aug(st)
+                name = "pi"
+            else:
+                name = "obs"
+            self._encode(name, B, False, st)  # post-critic-step PointNet weights; output detached
+            cat = w[f"cat_{name}"]
+            if S:
+                L.copy_cols(self.raw["obs"]["state"], S, 1, 1, cat, ld_cat, D, B, S, st)
+            self._mlp_fwd("actor", cat, D + S, B, w["out_pi"], 2 * A, 2 * A, "actor", st)
+            L.tanh_gaussian_fwd(w["out_pi"], B, A, hp.log_std_bound[0], hp.log_std_bound[1], hp.head_scale,
+                                hp.head_bias, noise.get("eps_pi"), self.seed, self.counter, 3, cat[:, D + S:], ld_cat,
+                                w["nlp_pi"], w["eps_pi"], st)
+            self._mlp_fwd("q0", cat, ld_cat, B, w["q_pi"], 2, 1, "q0", st)
+            self._mlp_fwd("q1", cat, ld_cat, B, w["q_pi"][:, 1:], 2, 1, "q1", st)
+            L.actor_loss(w["q_pi"], w["nlp_pi"], B, self.alpha_dev, p["log_alpha"], target_entropy, w["dq"],
+                         w["dlog_alpha"], self.scalars, st)
+            self._mlp_bwd("q0", cat, ld_cat, B, w["dq"], 2, 1, "q0", w["dx0"], False, st)
+            self._mlp_bwd("q1", cat, ld_cat, B, w["dq"][:, 1:], 2, 1, "q1", w["dx1"], False, st)
+            da = w["dx0"][:, D + S:]
+            L.add_cols(da, ld_cat, w["dx1"][:, D + S:], ld_cat, da, ld_cat, B, A, st)
+            L.tanh_gaussian_bwd_dev(w["out_pi"], w["eps_pi"], da, ld_cat, self.alpha_dev, B, A, hp.log_std_bound[0],
+                                    hp.log_std_bound[1], hp.head_scale, w["dout"], st)
+            a_lo, a_hi = self.layout.group_range["actor"]
+            self.grads[a_lo:a_hi].zero_()
+            self._mlp_bwd("actor", cat, D + S, B, w["dout"], 2 * A, 2 * A, "actor", None, True, st)
+            if self.allreduce is not None:
+                al_lo, al_hi = self.layout.group_range["alpha"]
+                self.allreduce(self.grads[a_lo:al_hi])  # actor grads | d log_alpha in one message
+            self._adam("actor", 1, hp.actor_lr, hp.betas, 8, False, st)
+            if hp.automatic_alpha_tuning:
+                self._adam("alpha", 2, hp.alpha_lr, hp.alpha_betas, None, False, st)
+                self.refresh_alpha()
+        self.counter.add_(1)
+
+    def _take_first_aug(self, st):
+        """xf_pi[b] = xf_obs[b*k] (and the bf16 tile images): strided device copies, no kernel."""
+        w, B, k = self.w, self.B, self.k
+        w["xf_pi"].copy_(w["xf_obs"].view(B, k, *w["xf_obs"].shape[1:])[:, 0])
+        if "xh_obs" in w:
+            w["xh_pi"].view(B, -1).copy_(w["xh_obs"].view(B, k, -1)[:, 0])
+
+    # ------------------------------------------------------------------ readback
+    def read_scalars(self, updates: int, sync=True):
+        """One device->host copy of everything update_parameters() logs (vs ~11 .item() syncs, sac.py:140-203)."""
+        if self.scalars_host is not None:
+            self.scalars_host.copy_(self.scalars, non_blocking=True)
+            if sync:
+                torch.cuda.current_stream().synchronize()
+            s = self.scalars_host.numpy().astype(np.float64)
+        else:
+            s = self.scalars.cpu().numpy().astype(np.float64)
+        hp = self.hp
+        pre = hp.algo
+        A = self.spec.action_dim
+        ret = {
+            f"{pre}/critic_loss": float(s[0]),
+            f"{pre}/max_critic_abs_err": float(s[1]),
+            f"{pre}/alpha": float(self._alpha_before),
+            f"{pre}/q": float(s[2]),
+            f"{pre}/q_target": float(s[3]),
+            f"{pre}/target_entropy": hp.target_entropy if hp.target_entropy is not None else -A,
+            f"{pre}/critic_grad": float(np.sqrt(s[4])),
+            f"{pre}/grad_steps": 1,
+        }
+        if updates % hp.actor_update_interval == 0:
+            ret[f"{pre}/actor_loss"] = float(s[5])
+            ret[f"{pre}/alpha_loss"] = float(s[6]) if hp.automatic_alpha_tuning else 0.0
+            ret[f"{pre}/entropy"] = float(s[7])
+            ret[f"{pre}/actor_grad"] = float(np.sqrt(s[8]))
+        self._alpha_before = float(s[9])
+        return ret
+
+    _alpha_before = 0.0
+
+    def prime_alpha(self):
+        """host copy of the cached alpha (the value update N logs is the one cached BEFORE update N, sac.py:152)."""
+        self._alpha_before = float(self.alpha_dev.item())

@@ -1,0 +1,277 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden vectors the
+reference itself produced.  Tolerances: north_star -- argmax bit-exact on the fp32 path (up to ties
+between values equal to within fp32 summation-order noise), features / Q-values / gradients within
+1e-3 relative in fp32, 2e-2 in bf16."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pointnet_sac_oracle as O
+from tests.conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+REL_FP32 = 1e-3
+REL_BF16 = 2e-2
+
+
+def rel_err(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def _t(tree):
+    return {k: torch.from_numpy(np.asarray(v)) for k, v in tree.items()}
+
+
+@pytest.fixture(scope="module")
+def L():
+    from pointcloud_rl_b200._lib import lib
+
+    assert torch.cuda.is_available()
+    return lib()
+
+
+def sp():
+    from pointcloud_rl_b200._lib import stream_ptr
+
+    return stream_ptr()
+
+
+# ------------------------------------------------------------------------------------------ dense
+@pytest.mark.parametrize("M,K,N,relu", [(512, 256, 1024, 1), (37, 141, 10, 0), (256, 1024, 1, 0), (1, 7, 128, 1)])
+def test_linear_fwd_bwd(L, M, K, N, relu):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K**0.5
+    b = torch.randn(N, generator=g)
+    dy = torch.randn(M, N, generator=g)
+    xr = x.clone().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y_ref = xr @ wr.t() + br
+    (y_ref * dy).sum().backward()
+    xd, wd, bd, dyd = x.cuda(), w.cuda(), b.cuda(), dy.cuda()
+    y = torch.empty(M, N, device="cuda")
+    L.linear_fwd(xd, K, wd, bd, y, N, M, K, N, relu, sp())
+    ref = torch.relu(y_ref) if relu else y_ref
+    assert rel_err(y, ref.detach()) < 1e-5
+    dw = torch.zeros(N, K, device="cuda")
+    db = torch.zeros(N, device="cuda")
+    dx = torch.empty(M, K, device="cuda")
+    L.linear_bwd(xd, K, wd, dyd, N, dw, db, dx, K, M, K, N, sp())
+    assert rel_err(dw, wr.grad) < 1e-5
+    assert rel_err(db, br.grad) < 1e-5
+    assert rel_err(dx, xr.grad) < 1e-5
+
+
+def test_layernorm_fwd_bwd(L):
+    g = torch.Generator().manual_seed(1)
+    M, D = 77, 128
+    x = torch.randn(M, D, generator=g) * 3 + 1
+    gam, bet = torch.randn(D, generator=g), torch.randn(D, generator=g)
+    dy = torch.randn(M, D, generator=g)
+    xr, gr, br = x.clone().requires_grad_(True), gam.clone().requires_grad_(True), bet.clone().requires_grad_(True)
+    y_ref = torch.nn.functional.layer_norm(xr, (D,), gr, br, 1e-5)
+    (y_ref * dy).sum().backward()
+    y = torch.empty(M, D, device="cuda")
+    xhat, rstd = torch.empty(M, D, device="cuda"), torch.empty(M, device="cuda")
+    L.layernorm_fwd(x.cuda(), gam.cuda(), bet.cuda(), y, D, xhat, rstd, M, D, 1e-5, sp())
+    assert rel_err(y, y_ref.detach()) < 1e-5
+    dg, db = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    dx = dy.cuda().clone()
+    L.layernorm_bwd(dx, D, xhat, rstd, gam.cuda(), dg, db, dx, M, D, sp())
+    assert rel_err(dx, xr.grad) < 1e-4
+    assert rel_err(dg, gr.grad) < 1e-5
+    assert rel_err(db, br.grad) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ policy head
+def test_tanh_gaussian_fwd_bwd(L):
+    g = torch.Generator().manual_seed(2)
+    M, A = 64, 7
+    out = torch.randn(M, 2 * A, generator=g)
+    out[:, A:] *= 4  # exercise the log-std clamp on both sides
+    out[0, A] = 2.0  # exactly on the bound: clamp passes gradient
+    eps = torch.randn(M, A, generator=g)
+    da = torch.randn(M, A, generator=g)
+    g_nlp = -0.3
+    o = out.clone().requires_grad_(True)
+    a_ref, nlp_ref = O.tanh_gaussian(o, eps)
+    ((a_ref * da).sum() + g_nlp * nlp_ref.sum()).backward()
+    act = torch.empty(M, A, device="cuda")
+    nlp, eps_out = torch.empty(M, device="cuda"), torch.empty(M, A, device="cuda")
+    L.tanh_gaussian_fwd(out.cuda(), M, A, -10.0, 2.0, 1.0, 0.0, eps.cuda(), 0, None, 0, act, A, nlp, eps_out, sp())
+    assert rel_err(act, a_ref.detach()) < 1e-5
+    assert rel_err(nlp, nlp_ref.detach()[:, 0]) < 1e-4
+    dout = torch.empty(M, 2 * A, device="cuda")
+    L.tanh_gaussian_bwd(out.cuda(), eps_out, da.cuda(), A, g_nlp, M, A, -10.0, 2.0, 1.0, dout, sp())
+    assert rel_err(dout, o.grad) < 1e-4
+    # Philox path: unit-variance, zero-mean noise
+    L.tanh_gaussian_fwd(torch.zeros(4096, 2 * A, device="cuda"), 4096, A, -10.0, 2.0, 1.0, 0.0, None, 123,
+                        torch.zeros(1, dtype=torch.int64, device="cuda"), 0, torch.empty(4096, A, device="cuda"), A,
+                        torch.empty(4096, device="cuda"), e2 := torch.empty(4096, A, device="cuda"), sp())
+    assert abs(float(e2.mean())) < 0.03 and abs(float(e2.std()) - 1) < 0.03
+
+
+# ------------------------------------------------------------------------------------------ staging
+@pytest.mark.parametrize("aug", ["none", "jitter", "rot"])
+def test_stage_points(L, aug):
+    rs = np.random.RandomState(3)
+    B, N, k = 5, 200, 2
+    obs = O.synthetic_obs(rs, B, N, n_seg=2, n_pos=0)
+    kind = {"none": 0, "jitter": 1, "rot": 2}[aug]
+    rep = k if kind else 1
+    t = {key: torch.from_numpy(v) for key, v in obs.items()}
+    rept = O._repeat_obs(t, rep)
+    noise = None
+    if aug == "jitter":
+        noise = torch.from_numpy(rs.uniform(-0.01, 0.01, size=(B * rep, 3, N)).astype(np.float32))
+        rept["xyz"] = O.aug_jitter(rept["xyz"], noise)
+    elif aug == "rot":
+        noise = torch.from_numpy(rs.uniform(-0.15, 0.15, size=(B * rep, 1)).astype(np.float32))
+        rept["xyz"] = O.aug_rot_z(rept["xyz"], noise)
+    x_ref = O.preprocess(rept)  # [R, C, N]
+    C, NP, CP = x_ref.shape[1], 256, 8
+    xf = torch.full((B * rep, NP, CP), 7.0, device="cuda")
+    L.stage_points(t["xyz"].cuda(), t["rgb"].cuda(), 1, None, 0, t["seg"].to(torch.uint8).cuda(), 2, B, N, rep, kind,
+                   -0.01, 0.01, noise.cuda() if noise is not None else None, 0, None, 0, xf, None, CP, sp())
+    got = xf[:, :N, :C].permute(0, 2, 1).cpu()
+    if aug == "rot":
+        assert torch.allclose(got, x_ref, atol=1e-6)
+    else:
+        assert torch.equal(got, x_ref)
+    assert float(xf[:, N:].abs().max()) == 0.0 and float(xf[:, :, C:].abs().max()) == 0.0
+
+
+def test_stage_points_philox_jitter_statistics(L):
+    B, N = 4, 1000
+    xyz = torch.zeros(B, 3, N, device="cuda")
+    xf = torch.zeros(B * 2, 1024, 8, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    L.stage_points(xyz, None, 0, None, 0, None, 0, B, N, 2, 1, -0.01, 0.01, None, 42, cnt, 0, xf, None, 8, sp())
+    j = xf[:, :N, :3]
+    assert float(j.min()) >= -0.01 and float(j.max()) <= 0.01
+    assert abs(float(j.mean())) < 2e-4 and abs(float(j.std()) - 0.02 / 12**0.5) < 2e-4
+    assert not torch.equal(j[0], j[1])  # the two augmentations of one sample differ
+    xf2 = torch.zeros_like(xf)
+    L.stage_points(xyz, None, 0, None, 0, None, 0, B, N, 2, 1, -0.01, 0.01, None, 42, cnt, 0, xf2, None, 8, sp())
+    assert torch.equal(xf, xf2)  # counter-based: same (seed, counter) -> same noise
+    cnt += 1
+    L.stage_points(xyz, None, 0, None, 0, None, 0, B, N, 2, 1, -0.01, 0.01, None, 42, cnt, 0, xf2, None, 8, sp())
+    assert not torch.equal(xf, xf2)
+
+
+# ------------------------------------------------------------------------------------------ PointNet
+def _pointnet_case(name):
+    g = load_golden(name)
+    p = _t(g["params"])
+    obs = _t(g["obs"])
+    return g, p, obs
+
+
+def _run_pointnet_f32(L, p, obs, want_argmax=True):
+    x = O.preprocess(obs)
+    R, C, N = x.shape
+    NP = (N + 127) // 128 * 128
+    CP = 8 if C <= 8 else 16
+    xf = torch.zeros(R, NP, CP, device="cuda")
+    seg = obs.get("seg")
+    pos = obs.get("pos_encoding")
+    L.stage_points(obs["xyz"].cuda(), obs["rgb"].cuda(), 1, pos.cuda() if pos is not None else None,
+                   0 if pos is None else pos.shape[1], seg.to(torch.uint8).cuda() if seg is not None else None,
+                   0 if seg is None else seg.shape[1], R, N, 1, 0, 0.0, 0.0, None, 0, None, 0, xf, None, CP, sp())
+    c1, c2, c3 = p["pn.w0"].shape[0], p["pn.w1"].shape[0], p["pn.w2"].shape[0]
+    d = {k: v.cuda().contiguous() for k, v in p.items()}
+    pooled = torch.empty(R, c3, device="cuda")
+    argmax = torch.empty(R, c3, dtype=torch.int32, device="cuda")
+    nbytes = int(L.pointnet_fwd_f32_workspace(2, NP, c1, c2, c3))  # 2 clouds per chunk: exercises chunking
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    L.pointnet_fwd_f32(xf, R, N, NP, CP, C, d["pn.w0"], d["pn.b0"], d["pn.w1"], d["pn.g1"], d["pn.be1"], d["pn.w2"],
+                       d["pn.g2"], d["pn.be2"], c1, c2, c3, 1e-6, pooled, argmax, ws, nbytes, sp())
+    return x, xf, d, pooled, argmax, (R, N, NP, CP, C, c1, c2, c3)
+
+
+@pytest.mark.parametrize("name", ["pointnet_fwd_c7", "pointnet_fwd_c7_dup", "pointnet_fwd_c9_dmc"])
+def test_pointnet_fwd_f32_matches_reference(L, name):
+    g, p, obs = _pointnet_case(name)
+    x, xf, d, pooled, argmax, _ = _run_pointnet_f32(L, p, obs)
+    ref_pooled, ref_idx = torch.from_numpy(g["pooled"]), torch.from_numpy(g["idx"])
+    assert rel_err(pooled, ref_pooled) < 1e-5
+    idx = argmax.cpu().long()
+    mism = idx != ref_idx
+    # fp32 path: argmax identical except where two candidates are equal to within summation-order noise
+    assert mism.float().mean() < 5e-3
+    if mism.any():
+        h = O.pointnet_point_features(p, x)
+        v_ours = torch.gather(h, 2, idx[..., None])[..., 0][mism]
+        v_ref = torch.gather(h, 2, ref_idx[..., None])[..., 0][mism]
+        assert torch.allclose(v_ours, v_ref, rtol=2e-5, atol=1e-6)
+    if name.endswith("dup"):
+        N = obs["xyz"].shape[-1]
+        assert int(idx.max()) < N - N // 4  # exact duplicates: ties resolve to the smallest index
+
+
+def test_pointnet_bwd_sparse_matches_autograd(L):
+    g, p, obs = _pointnet_case("pointnet_fwd_c7")
+    x, xf, d, pooled, argmax, (R, N, NP, CP, C, c1, c2, c3) = _run_pointnet_f32(L, p, obs)
+    gen = torch.Generator().manual_seed(5)
+    dpool = torch.randn(R, c3, generator=gen)
+    keys = ["pn.w0", "pn.b0", "pn.w1", "pn.g1", "pn.be1", "pn.w2", "pn.g2", "pn.be2"]
+    leaves = {k: p[k].clone().requires_grad_(True) for k in keys}
+    h = O.pointnet_point_features(leaves, x)
+    (h.max(-1)[0] * dpool).sum().backward()
+    grads = {k: torch.zeros_like(d[k]) for k in keys}
+    nbytes = int(L.pointnet_bwd_workspace(R, NP, c1, c2, c3, CP))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    L.pointnet_bwd(xf, R, N, NP, CP, C, pooled, argmax, dpool.cuda(), d["pn.w0"], d["pn.b0"], d["pn.w1"], d["pn.g1"],
+                   d["pn.be1"], d["pn.w2"], d["pn.g2"], d["pn.be2"], c1, c2, c3, 1e-6, *[grads[k] for k in keys], ws,
+                   nbytes, sp())
+    for k in keys:
+        assert rel_err(grads[k], leaves[k].grad) < REL_FP32, k
+
+
+# ------------------------------------------------------------------------------------------ full update
+def _engine_from_golden(g, precision="fp32"):
+    from pointcloud_rl_b200.engine import HyperParams, PathSpec, UpdateEngine
+
+    m = {k: v.item() for k, v in g["meta"].items()}
+    init = _t(g["init"])
+    c1, c2, c3 = init["pn.w0"].shape[0], init["pn.w1"].shape[0], init["pn.w2"].shape[0]
+    spec = PathSpec(n_points=m["N"], action_dim=m["A"], state_dim=m["S"], n_pos=m["n_pos"], n_seg=m["n_seg"],
+                    widths=(c1, c2, c3), out_dim=init["pn.wf"].shape[0],
+                    hidden=(init["actor.w0"].shape[0], init["actor.w1"].shape[0]))
+    hp = HyperParams(algo=m["algo"], gamma=m["gamma"], reward_scale=m["reward_scale"], num_aug=m["num_aug"],
+                     aug=m["aug"] or None, aug_lo=m["aug_lo"], aug_hi=m["aug_hi"], tau=m["tau"],
+                     actor_update_interval=m["actor_update_interval"],
+                     target_update_interval=m["target_update_interval"], target_entropy=m["target_entropy"])
+    eng = UpdateEngine(spec, hp, batch_size=m["B"], precision=precision)
+    eng.load_params(init)
+    eng.prime_alpha()
+    return eng, m
+
+
+@pytest.mark.parametrize("name", ["sac_dmc_small", "drq_jitter_small", "drq_rot_small"])
+def test_update_matches_reference_fp32(name):
+    g = load_golden(name)
+    eng, m = _engine_from_golden(g)
+    eng.upload_batch(g["batch"])
+    for u in range(1, m["n_updates"] + 1):
+        noise = {k: v.cuda() for k, v in _t(g[f"noise{u}"]).items()}
+        if "angle_obs" in noise:
+            noise = {k: (v.reshape(-1) if k.startswith("angle") else v) for k, v in noise.items()}
+        eng.update(u, noise)
+        ret = eng.read_scalars(u)
+        ref = {f"{a}/{b}": float(v) for a, sub in g[f"ret{u}"].items() for b, v in sub.items()}
+        assert set(ret) == set(ref)
+        for key, val in ref.items():
+            assert ret[key] == pytest.approx(val, rel=REL_FP32, abs=1e-4), (u, key)
+        after = _t(g[f"after{u}"])
+        got = eng.export_params()
+        init = _t(g["init"])
+        for key, val in after.items():
+            # compare the applied parameter change: Adam's first steps are ~lr-sized whatever the gradient
+            # scale, so an element whose gradient is at rounding-noise level may legitimately move the
+            # other way; judge the update as a whole (norm-wise) and bound every element by 2*lr*u
+            delta_ref, delta = val - init[key], got[key] - init[key]
+            assert rel_err(delta, delta_ref) < 2e-2, (u, key, rel_err(delta, delta_ref))
+            assert float((delta - delta_ref).abs().max()) <= 2.1e-3 * u, (u, key)
