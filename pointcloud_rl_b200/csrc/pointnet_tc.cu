@@ -1,15 +1,494 @@
-// placeholder until the tcgen05 kernel lands (next commit)
+// Fused PointNet per-point MLP + max-pool on the 5th-gen tensor cores (tcgen05 / TMEM), sm_100a.
+//
+//   per 128-point tile:  acc0 = X W0'^T          (K=16: channels | 1 (bias) | xyz lo parts)   -> relu    -> h0 (bf16, smem)
+//                        acc1 = h0 W1^T          -> LN over channels (thread-local) + relu   -> h1 (bf16, smem)
+//                        acc2 = h1 W2^T          -> LN + relu -> max / argmax over the tile's points
+//                        (key, ~index) packed u64 -> atomicMax into the cloud's pooled row
+//
+// Points sit on the MMA M axis (128 TMEM lanes = 128 points), channels along TMEM columns, so after a
+// 32x32b tcgen05.ld every thread owns one point's channel row: LayerNorm statistics are thread-local
+// and the max over points is the cross-lane direction (redux.sync + ballot).
+//
+// Persistent kernel, one CTA per SM, 10 warps:
+//   warp 0      TMA producer: weights once (cp.async.bulk), then the 4 KB point tiles through a 4-stage ring
+//   warp 1      MMA issuer (one elected thread), ping-pongs two tile slots
+//   warps 2-5   epilogue of slot 0   } each slot owns 256 TMEM columns and one activation buffer; while one
+//   warps 6-9   epilogue of slot 1   } slot's epilogue normalises layer k, the tensor core runs the other slot
+//
+// All operands use the no-swizzle K-major UMMA canonical layout (8x16B core matrices, LBO = 128 B
+// between K-adjacent cores, SBO = K*16 B between 8-row groups); the staging kernel and the weight
+// packer write global memory in exactly that byte image so plain 1-D bulk copies land MMA-ready tiles.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
+
+namespace pcrl {
+namespace tc {
+
+constexpr int kStages = 4;
+constexpr int kTileBytes = 128 * 16 * 2;  // one X tile: 128 points x 16 bf16
+constexpr int kThreads = 320;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// K-major, no swizzle: LBO = 128 B (K-adjacent core matrices), SBO = K*16 B (8-row groups). version=1 (sm_100).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(128u >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// kind::f16, A=B=BF16, D=F32, both K-major, M=128
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// two fp32 -> packed bf16x2 with ReLU; `lo` lands in the low half (lower channel / lower address)
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+struct SmemLayout {
+  uint32_t w0, w1, w2, prm, xst, act, wkey, bars, total;
+};
+__host__ __device__ inline SmemLayout make_layout(int c1, int c2, int c3) {
+  SmemLayout L;
+  uint32_t o = 0;
+  L.w0 = o;   o += c1 * 32;
+  L.w1 = o;   o += c2 * c1 * 2;
+  L.w2 = o;   o += c3 * c2 * 2;
+  L.prm = o;  o += (2 * c2 + 2 * c3) * 4;
+  o = (o + 127) & ~127u;
+  L.xst = o;  o += kStages * kTileBytes;
+  const int kmax = c1 > c2 ? c1 : c2;
+  L.act = o;  o += 2 * 128 * kmax * 2;
+  L.wkey = o; o += 2 * 4 * c3 * 8;
+  L.bars = o; o += 128;
+  L.total = o;
+  return L;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpack, int n_tiles, int tiles_per_cloud,
+                       int N, int c1, int c2, int c3, float ln_eps, int want_argmax,
+                       unsigned long long* __restrict__ pool_keys) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const SmemLayout L = make_layout(c1, c2, c3);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // barriers: [0] weights, [1..4] xfull, [5..8] xempty, [9,10] accfull, [11,12] actready; then tmem ptr
+  const uint32_t bar0 = sbase + L.bars;
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L.bars + 13 * 8);
+
+  if (threadIdx.x == 0) {
+    mbar_init(BAR(0), 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(BAR(1 + s), 1);
+      mbar_init(BAR(5 + s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(BAR(9 + s), 1);
+      mbar_init(BAR(11 + s), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
+        smem_u32((const void*)tmem_ptr_smem)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int n_local = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint32_t wbytes = (uint32_t)(c1 * 32 + c2 * c1 * 2 + c3 * c2 * 2 + (2 * c2 + 2 * c3) * 4);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(BAR(0), wbytes);
+      // weights + LN parameters are one contiguous image laid out exactly like the smem carve-up
+      uint32_t off = 0;
+      while (off < wbytes) {
+        uint32_t n = min(wbytes - off, 32768u);
+        bulk_g2s(sbase + L.w0 + off, wpack + off, n, BAR(0));
+        off += n;
+      }
+      for (int i = 0; i < n_local; ++i) {
+        const int st = i % kStages;
+        if (i >= kStages) mbar_wait(BAR(5 + st), ((i / kStages) - 1) & 1);
+        mbar_expect_tx(BAR(1 + st), kTileBytes);
+        const int64_t tile = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
+        bulk_g2s(sbase + L.xst + st * kTileBytes, xh + tile * kTileBytes, kTileBytes, BAR(1 + st));
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      mbar_wait(BAR(0), 0);
+      uint32_t ph_act[2] = {0, 0};
+      const uint32_t id0 = make_idesc(c1), id1 = make_idesc(c2), id2 = make_idesc(c3);
+      const int kmax = c1 > c2 ? c1 : c2;
+      for (int p = 0; 2 * p < n_local; ++p) {
+#pragma unroll 1
+        for (int layer = 0; layer < 3; ++layer) {
+#pragma unroll 1
+          for (int s = 0; s < 2; ++s) {
+            const int i = 2 * p + s;
+            if (i >= n_local) continue;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(s * 256);
+            const uint32_t act = sbase + L.act + (uint32_t)(s * 128 * kmax * 2);
+            if (layer == 0) {
+              const int st = i % kStages;
+              mbar_wait(BAR(1 + st), (i / kStages) & 1);
+              if (p > 0) {  // previous tile's layer-2 accumulator must be drained
+                mbar_wait(BAR(11 + s), ph_act[s] & 1);
+                ph_act[s]++;
+              }
+              tc_fence_after();
+              mma_bf16(d_tmem, make_desc(sbase + L.xst + st * kTileBytes, 256), make_desc(sbase + L.w0, 256), id0, 0);
+              mma_commit(BAR(5 + st));
+            } else {
+              mbar_wait(BAR(11 + s), ph_act[s] & 1);
+              ph_act[s]++;
+              tc_fence_after();
+              const int K = (layer == 1) ? c1 : c2;
+              const uint32_t wb = sbase + ((layer == 1) ? L.w1 : L.w2);
+              const uint32_t idesc = (layer == 1) ? id1 : id2;
+              for (int ks = 0; ks < K / 16; ++ks)
+                mma_bf16(d_tmem, make_desc(act + ks * 256, K * 16), make_desc(wb + ks * 256, K * 16), idesc, ks > 0);
+            }
+            mma_commit(BAR(9 + s));
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int s = (warp - 2) >> 2;       // slot
+    const int q = warp & 3;              // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;       // point within the tile
+    const int kmax = c1 > c2 ? c1 : c2;
+    unsigned char* act = smem + L.act + s * 128 * kmax * 2;
+    const float* prm = reinterpret_cast<const float*>(smem + L.prm);
+    const float *g1 = prm, *be1 = prm + c2, *g2 = prm + 2 * c2, *be2 = prm + 2 * c2 + c3;
+    unsigned long long* wkey = reinterpret_cast<unsigned long long*>(smem + L.wkey) + (s * 4 + q) * c3;
+    const unsigned long long* wkey_slot = reinterpret_cast<unsigned long long*>(smem + L.wkey) + s * 4 * c3;
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 256);
+    const int tid_slot = threadIdx.x - (64 + s * 128);
+    uint32_t ph_acc = 0;
+    mbar_wait(BAR(0), 0);  // LN parameters landed
+
+    for (int i = s; i < n_local; i += 2) {
+      const int64_t tile = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
+      const int cloud = (int)(tile / tiles_per_cloud);
+      const int n_in_cloud = (int)(tile % tiles_per_cloud) * 128 + row;
+      uint32_t v[32];
+
+      // ---- layer 0: relu -> bf16 -> activation buffer (K = c1)
+      mbar_wait(BAR(9 + s), ph_acc & 1);
+      ph_acc++;
+      tc_fence_after();
+      {
+        const uint32_t sbo = (uint32_t)c1 * 16;
+        unsigned char* dst = act + (row >> 3) * sbo + (row & 7) * 16;
+        for (int ch = 0; ch < c1; ch += 32) {
+          tmem_ld32(taddr0 + ch, v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_relu_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+            o.y = pack_relu_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+            o.z = pack_relu_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+            o.w = pack_relu_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+            *reinterpret_cast<uint4*>(dst + ((ch >> 3) + j) * 128) = o;
+          }
+        }
+      }
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive(BAR(11 + s));
+
+      // ---- layer 1: LN over channels (thread-local) + relu -> bf16 -> activation buffer (K = c2)
+      mbar_wait(BAR(9 + s), ph_acc & 1);
+      ph_acc++;
+      tc_fence_after();
+      {
+        float sum = 0.f, sq = 0.f;
+        for (int ch = 0; ch < c2; ch += 32) {
+          tmem_ld32(taddr0 + ch, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float y = __uint_as_float(v[j]);
+            sum += y;
+            sq = fmaf(y, y, sq);
+          }
+        }
+        const float mean = sum / (float)c2;
+        const float var = fmaxf(sq / (float)c2 - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + ln_eps);
+        const float nmr = -mean * rstd;
+        const uint32_t sbo = (uint32_t)c2 * 16;
+        unsigned char* dst = act + (row >> 3) * sbo + (row & 7) * 16;
+        for (int ch = 0; ch < c2; ch += 32) {
+          tmem_ld32(taddr0 + ch, v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 ga = *reinterpret_cast<const float4*>(g1 + ch + 8 * j);
+            const float4 gb = *reinterpret_cast<const float4*>(g1 + ch + 8 * j + 4);
+            const float4 ba = *reinterpret_cast<const float4*>(be1 + ch + 8 * j);
+            const float4 bb = *reinterpret_cast<const float4*>(be1 + ch + 8 * j + 4);
+            const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+            const float bbv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = fmaf(fmaf(__uint_as_float(v[8 * j + e]), rstd, nmr), gg[e], bbv[e]);
+            uint4 pk;
+            pk.x = pack_relu_bf16x2(o[0], o[1]);
+            pk.y = pack_relu_bf16x2(o[2], o[3]);
+            pk.z = pack_relu_bf16x2(o[4], o[5]);
+            pk.w = pack_relu_bf16x2(o[6], o[7]);
+            *reinterpret_cast<uint4*>(dst + ((ch >> 3) + j) * 128) = pk;
+          }
+        }
+      }
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive(BAR(11 + s));
+
+      // ---- layer 2: LN + relu, max (and argmax) over the tile's points
+      mbar_wait(BAR(9 + s), ph_acc & 1);
+      ph_acc++;
+      tc_fence_after();
+      {
+        float sum = 0.f, sq = 0.f;
+        for (int ch = 0; ch < c3; ch += 32) {
+          tmem_ld32(taddr0 + ch, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float y = __uint_as_float(v[j]);
+            sum += y;
+            sq = fmaf(y, y, sq);
+          }
+        }
+        const float mean = sum / (float)c3;
+        const float var = fmaxf(sq / (float)c3 - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + ln_eps);
+        const float nmr = -mean * rstd;
+        const bool valid = n_in_cloud < N;
+        named_bar(1 + s, 128);  // previous tile's combine has finished reading wkey
+        for (int ch = 0; ch < c3; ch += 32) {
+          tmem_ld32(taddr0 + ch, v);
+          uint32_t my_key = 0, my_lane = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float o = fmaf(fmaf(__uint_as_float(v[j]), rstd, nmr), g2[ch + j], be2[ch + j]);
+            o = valid ? fmaxf(o, 0.f) : 0.f;
+            const uint32_t bits = __float_as_uint(o);  // o >= 0: bit pattern is order-preserving
+            const uint32_t m = __reduce_max_sync(0xffffffffu, bits);
+            uint32_t win = 0;
+            if (want_argmax) win = __ffs(__ballot_sync(0xffffffffu, bits == m)) - 1;  // lowest lane = smallest index
+            if (lane == j) {
+              my_key = m;
+              my_lane = win;
+            }
+          }
+          const uint32_t idx = (uint32_t)((int)(tile % tiles_per_cloud) * 128 + q * 32) + my_lane;
+          wkey[ch + lane] = ((unsigned long long)my_key << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+        }
+        tc_fence_before();
+        mbar_arrive(BAR(11 + s));  // accumulator drained: the MMA warp may start this slot's next tile
+        named_bar(1 + s, 128);
+        for (int c = tid_slot; c < c3; c += 128) {
+          unsigned long long k = wkey_slot[c];
+          k = max(k, wkey_slot[c3 + c]);
+          k = max(k, wkey_slot[2 * c3 + c]);
+          k = max(k, wkey_slot[3 * c3 + c]);
+          atomicMax(pool_keys + (int64_t)cloud * c3 + c, k);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+  }
+}
+
+__global__ void pool_finalize_kernel(const unsigned long long* __restrict__ keys, int64_t n, float* __restrict__ pooled,
+                                     int32_t* __restrict__ argmax) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long k = keys[i];
+  pooled[i] = __uint_as_float((uint32_t)(k >> 32));
+  if (argmax) argmax[i] = (int32_t)(0xFFFFFFFFu - (uint32_t)k);
+}
+
+// byte offset of element (row n, k) in a K-major no-swizzle image with K columns
+__device__ __forceinline__ uint32_t img_off(int n, int k, int K) {
+  return (uint32_t)((n >> 3) * (K * 16) + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2);
+}
+
+__global__ void pack_weights_kernel(const float* __restrict__ w0, const float* __restrict__ b0,
+                                    const float* __restrict__ w1, const float* __restrict__ g1,
+                                    const float* __restrict__ be1, const float* __restrict__ w2,
+                                    const float* __restrict__ g2, const float* __restrict__ be2, int C, int c1, int c2,
+                                    int c3, int rgb_u8, char* __restrict__ out) {
+  const int n0 = c1 * 16, n1 = c2 * c1, n2 = c3 * c2, n3 = 2 * c2 + 2 * c3;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n0) {
+    const int n = i / 16, k = i % 16;
+    float v = 0.f;
+    if (k < C) {
+      v = w0[n * C + k];
+      if (rgb_u8 && k >= 3 && k < 6) v *= (1.0f / 255.0f);  // staged rgb is the raw 0..255 integer
+    } else if (k == C) {
+      v = b0[n];  // multiplies the constant-1 channel
+    } else if (k <= C + 3) {
+      v = w0[n * C + (k - C - 1)];  // lo parts of xyz see the same weights
+    }
+    *reinterpret_cast<__nv_bfloat16*>(out + img_off(n, k, 16)) = __float2bfloat16(v);
+  } else if (i < n0 + n1) {
+    const int e = i - n0, n = e / c1, k = e % c1;
+    *reinterpret_cast<__nv_bfloat16*>(out + c1 * 32 + img_off(n, k, c1)) = __float2bfloat16(w1[e]);
+  } else if (i < n0 + n1 + n2) {
+    const int e = i - n0 - n1, n = e / c2, k = e % c2;
+    *reinterpret_cast<__nv_bfloat16*>(out + c1 * 32 + c2 * c1 * 2 + img_off(n, k, c2)) = __float2bfloat16(w2[e]);
+  } else if (i < n0 + n1 + n2 + n3) {
+    const int e = i - n0 - n1 - n2;
+    float v;
+    if (e < c2) v = g1[e];
+    else if (e < 2 * c2) v = be1[e - c2];
+    else if (e < 2 * c2 + c3) v = g2[e - 2 * c2];
+    else v = be2[e - 2 * c2 - c3];
+    reinterpret_cast<float*>(out + c1 * 32 + c2 * c1 * 2 + c3 * c2 * 2)[e] = v;
+  }
+}
+
+static bool shapes_ok(int c1, int c2, int c3) {
+  auto ok = [](int c) { return c >= 32 && c <= 256 && c % 32 == 0; };
+  return ok(c1) && ok(c2) && ok(c3) && make_layout(c1, c2, c3).total <= 227 * 1024;
+}
+
+}  // namespace tc
+}  // namespace pcrl
+
+using namespace pcrl;
+
 extern "C" {
-int64_t pcrl_pointnet_wpack_bytes(int c1, int c2, int c3) { return 0; }
-int pcrl_pointnet_pack_weights(const float*, const float*, const float*, const float*, const float*, const float*,
-                               const float*, const float*, int, int, int, int, int, void*, void*) {
-  pcrl::set_error("bf16 path not built");
-  return PCRL_EUNSUPPORTED;
+
+int64_t pcrl_pointnet_wpack_bytes(int c1, int c2, int c3) {
+  return (int64_t)c1 * 32 + (int64_t)c2 * c1 * 2 + (int64_t)c3 * c2 * 2 + (2 * c2 + 2 * c3) * 4;
 }
-int pcrl_pointnet_fwd_bf16(const void*, int, int, int, const void*, int, int, int, float, uint64_t*, float*, int32_t*,
-                           void*) {
-  pcrl::set_error("bf16 path not built");
-  return PCRL_EUNSUPPORTED;
+
+int pcrl_pointnet_pack_weights(const float* w0, const float* b0, const float* w1, const float* g1, const float* be1,
+                               const float* w2, const float* g2, const float* be2, int C, int c1, int c2, int c3,
+                               int rgb_u8, void* wpack, void* stream) {
+  PCRL_CHECK_ARG(w0 && b0 && w1 && g1 && be1 && w2 && g2 && be2 && wpack);
+  PCRL_CHECK_ARG(C + 4 <= 16 && tc::shapes_ok(c1, c2, c3));
+  const int n = c1 * 16 + c2 * c1 + c3 * c2 + 2 * c2 + 2 * c3;
+  tc::pack_weights_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(w0, b0, w1, g1, be1, w2, g2, be2, C,
+                                                                                   c1, c2, c3, rgb_u8, (char*)wpack);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
 }
+
+int pcrl_pointnet_fwd_bf16(const void* xh, int R, int N, int NP, const void* wpack, int c1, int c2, int c3,
+                           float ln_eps, uint64_t* pool_keys, float* pooled, int32_t* argmax, void* stream) {
+  PCRL_CHECK_ARG(xh && wpack && pool_keys && pooled && R >= 0 && N > 0 && NP >= N && NP % 128 == 0);
+  if (!tc::shapes_ok(c1, c2, c3)) {
+    set_error("pcrl_pointnet_fwd_bf16: widths (%d,%d,%d) unsupported (multiples of 32 in [32,256], smem budget)", c1,
+              c2, c3);
+    return PCRL_EUNSUPPORTED;
+  }
+  if (R == 0) return PCRL_OK;
+  cudaStream_t st = as_stream(stream);
+  const tc::SmemLayout L = tc::make_layout(c1, c2, c3);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PCRL_CHECK_CUDA(cudaFuncSetAttribute(tc::pointnet_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024));
+    attr_set = true;
+  }
+  const int tiles_per_cloud = NP / 128;
+  const int n_tiles = R * tiles_per_cloud;
+  PCRL_CHECK_CUDA(cudaMemsetAsync(pool_keys, 0, (int64_t)R * c3 * sizeof(uint64_t), st));
+  const int grid = std::min(sm_count(), n_tiles);
+  tc::pointnet_fwd_tc_kernel<<<grid, tc::kThreads, L.total, st>>>((const char*)xh, (const char*)wpack, n_tiles,
+                                                                  tiles_per_cloud, N, c1, c2, c3, ln_eps,
+                                                                  argmax != nullptr,
+                                                                  (unsigned long long*)pool_keys);
+  PCRL_CHECK_LAUNCH();
+  const int64_t n = (int64_t)R * c3;
+  tc::pool_finalize_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>((const unsigned long long*)pool_keys, n, pooled,
+                                                                   argmax);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
 }
+
+}  // extern "C"
