@@ -233,7 +233,9 @@ class UpdateEngine:
             w["wpack"] = torch.zeros(int(self.L.pointnet_wpack_bytes(c1, c2, c3)), dtype=torch.uint8, device=dev)
             w["pool_keys"] = torch.zeros(R * c3, dtype=torch.int64, device=dev)
         self.w = w
-        self._wpack_dirty = True
+        self._graphs = {}
+        self.graph_calls = {}
+        self._landing = None
 
     # ------------------------------------------------------------------ parameters
     def load_params(self, params: Dict[str, torch.Tensor]):
@@ -246,7 +248,6 @@ class UpdateEngine:
                 raise KeyError(f"missing parameter {name}")
             view.copy_(torch.as_tensor(src, dtype=torch.float32).reshape(view.shape))
         self.refresh_alpha()
-        self._wpack_dirty = True
 
     def export_params(self):
         return {k: v.detach().clone().cpu() for k, v in self.p.items()}
@@ -310,11 +311,6 @@ class UpdateEngine:
         c1, c2, c3 = sp.widths
         argmax = w["argmax_obs"] if want_argmax else None
         if self.precision == "bf16":
-            if self._wpack_dirty:
-                self.L.pointnet_pack_weights(p["pn.w0"], p["pn.b0"], p["pn.w1"], p["pn.g1"], p["pn.be1"], p["pn.w2"],
-                                             p["pn.g2"], p["pn.be2"], sp.C, c1, c2, c3,
-                                             int(sp.has_rgb and sp.rgb_u8), w["wpack"], st)
-                self._wpack_dirty = False
             self.L.pointnet_fwd_bf16(w[f"xh_{name}"], rows, sp.n_points, sp.NP, w["wpack"], c1, c2, c3, sp.ln_eps,
                                      w["pool_keys"], w[f"pooled_{name}"], argmax, st)
         else:
@@ -328,6 +324,16 @@ class UpdateEngine:
         self.L.layernorm_fwd(w[f"z_{name}"], p["pn.gf"], p["pn.bef"], cat, cat.stride(0),
                              w["xhat_obs"] if save else None, w["rstd_obs"] if save else None, rows, D,
                              sp.head_ln_eps, st)
+
+    def _pack_weights(self, st):
+        """bf16 path: re-pack the (just updated) PointNet weights into the MMA-ready smem image."""
+        if self.precision != "bf16":
+            return
+        sp, p = self.spec, self.p
+        c1, c2, c3 = sp.widths
+        self.L.pointnet_pack_weights(p["pn.w0"], p["pn.b0"], p["pn.w1"], p["pn.g1"], p["pn.be1"], p["pn.w2"],
+                                     p["pn.g2"], p["pn.be2"], sp.C, c1, c2, c3, int(sp.has_rgb and sp.rgb_u8),
+                                     self.w["wpack"], st)
 
     def _mlp_fwd(self, net, x, K, M, out, ldo, nout, keep, st):
         p, (h1n, h2n) = self.p, self.spec.hidden
@@ -378,6 +384,7 @@ class UpdateEngine:
         ld_cat = D + S + A
         target_entropy = float(hp.target_entropy) if hp.target_entropy is not None else -float(A)
 
+        self._pack_weights(st)
         # ---- staging (+ augmentation fused into the load)
         self._stage("next_obs", "next", k, aug, noise.get(f"{nkey}_next") if nkey else None, 1, st)
         self._stage("obs", "obs", k, aug, noise.get(f"{nkey}_obs") if nkey else None, 0, st)
@@ -422,7 +429,6 @@ class UpdateEngine:
         if self.allreduce is not None:
             self.allreduce(self.grads[c_lo:c_hi])
         self._adam("critic", 0, hp.lr, hp.betas, 4, do_target, st)  # + Polyak fused (sac.py:207-208)
-        self._wpack_dirty = True
 
         # ---- actor + alpha step: sac.py:161-205 / drq.py:114-155
         if do_actor:
@@ -431,6 +437,7 @@ class UpdateEngine:
                 name = "pi"
             else:
                 name = "obs"
+            self._pack_weights(st)
             self._encode(name, B, False, st)  # post-critic-step PointNet weights; output detached
             cat = w[f"cat_{name}"]
             if S:
@@ -460,6 +467,65 @@ class UpdateEngine:
                 self._adam("alpha", 2, hp.alpha_lr, hp.alpha_betas, None, False, st)
                 self.refresh_alpha()
         self.counter.add_(1)
+
+    # ------------------------------------------------------------------ CUDA graphs
+    def update_graphed(self, updates: int):
+        """Same as update() (Philox randomness only) but replayed from a CUDA graph: one launch per update
+        instead of ~150.  Two graphs exist at most per (actor step?, target step?) combination."""
+        hp = self.hp
+        key = (updates % hp.actor_update_interval == 0, updates % hp.target_update_interval == 0)
+        g = self._graphs.get(key)
+        if g is None:
+            # warm-up outside capture (module loading, cudaFuncSetAttribute), on a side stream as torch requires
+            state = (self.params.clone(), self.adam_m.clone(), self.adam_v.clone(), self.steps.clone(),
+                     self.counter.clone(), self.alpha_dev.clone(), self.scalars.clone())
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.update(updates)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            for dst, src in zip((self.params, self.adam_m, self.adam_v, self.steps, self.counter, self.alpha_dev,
+                                 self.scalars), state):
+                dst.copy_(src)
+            g = torch.cuda.CUDAGraph()
+            n0 = self.L.launches
+            with torch.cuda.graph(g):
+                self.update(updates)
+            self.graph_calls[key] = self.L.launches - n0  # C-ABI calls (>= 1 kernel each) replayed per launch
+            # capture does not execute: state is untouched
+            self._graphs[key] = g
+        g.replay()
+        return self.graph_calls[key]
+
+    # ------------------------------------------------------------------ pipelined host->device input path
+    def make_pinned_batch(self, batch):
+        """The replay sample laid out in pinned host memory (what a pinned replay ring would hand over)."""
+        return {k: v.contiguous().pin_memory() for k, v in self._flatten_batch(batch).items()}
+
+    def h2d_async(self, pinned, slot, copy_stream):
+        """Enqueue the H2D copies of one batch into landing buffer `slot` on `copy_stream`; returns (event, bytes)."""
+        if self._landing is None:
+            self._landing = [{k: torch.empty_like(self._device_leaf(k)) for k in pinned} for _ in range(2)]
+        nbytes = 0
+        with torch.cuda.stream(copy_stream):
+            for k, src in pinned.items():
+                self._landing[slot][k].copy_(src, non_blocking=True)
+                nbytes += src.numel() * src.element_size()
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ev, nbytes
+
+    def adopt(self, slot, event):
+        """Make landing buffer `slot` the current batch (device-to-device, on the current stream)."""
+        torch.cuda.current_stream().wait_event(event)
+        for k, src in self._landing[slot].items():
+            self._device_leaf(k).copy_(src, non_blocking=True)
+
+    def set_batch_device(self, dev_batch):
+        """Batch already resident in HBM (flattened keys as make_pinned_batch): device-to-device adopt."""
+        for k, src in dev_batch.items():
+            self._device_leaf(k).copy_(src, non_blocking=True)
 
     def _take_first_aug(self, st):
         """xf_pi[b] = xf_obs[b*k] (and the bf16 tile images): strided device copies, no kernel."""
