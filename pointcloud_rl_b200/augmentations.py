@@ -1,0 +1,108 @@
+"""Point-cloud augmentation registry entries (pyrl/utils/augmentations/{builder,pcd_aug}.py).
+
+On the update path these objects are *descriptors*: DrQ reads them and the staging kernel applies the
+augmentation fused into the load (pcrl_stage_points).  Calling one directly on a dict of device tensors
+(DrQ.inference_aug, drq.py:33-44) runs the same kernel-side arithmetic via torch ops on xyz only."""
+import torch
+
+from .meta import Registry, build_from_cfg
+
+AUGMENTATIONS = Registry("data augmentation")
+
+
+class BaseAugmentation:
+    kind = None  # engine aug name
+
+    def __init__(self, main_key=None, req_keys=None):
+        self.main_key = main_key
+        self.req_keys = req_keys or [main_key]
+        assert main_key in self.req_keys, f"{main_key}, {req_keys} do not satisfy the requirement!"
+
+    def params(self):
+        raise NotImplementedError
+
+
+@AUGMENTATIONS.register_module()
+class RandomJitterPoints(BaseAugmentation):
+    """xyz += U(lo, hi) i.i.d. per coordinate per point (pcd_aug.py:307-322)."""
+
+    kind = "jitter"
+
+    def __init__(self, main_key="inputs/xyz", req_keys=None, jitter_range=[-0.1, 0.1]):
+        super().__init__(main_key, req_keys)
+        self.jitter_range = [float(jitter_range[0]), float(jitter_range[1])]
+
+    def params(self):
+        return self.kind, self.jitter_range[0], self.jitter_range[1]
+
+    def __call__(self, data):
+        data = dict(data)
+        for key in self.req_keys:
+            if key in data:
+                x = data[key]
+                lo, hi = self.jitter_range
+                data[key] = x + (torch.rand_like(x) * (hi - lo) + lo)
+        return data
+
+    def __repr__(self):
+        return f"RandomJitterPoints(jitter_range={self.jitter_range})"
+
+
+@AUGMENTATIONS.register_module()
+class GlobalRotScaleTrans(BaseAugmentation):
+    """Per-cloud z-rotation by U(rot_range) (pcd_aug.py:126-215).  Rotation-only subset (`pn_rot.py`);
+    scaling / translation raise (SURVEY.md section 8f lists them as the next widening step)."""
+
+    kind = "rot"
+
+    def __init__(self, main_key=None, req_keys=None, rot_range=[-0.78539816, 0.78539816], rot_axis="z",
+                 scale_ratio_range=[0.95, 1.05], translation_range=[0, 0, 0], shift_height=False):
+        main_key = main_key[0] if isinstance(main_key, (list, tuple)) else main_key
+        super().__init__(main_key, req_keys)
+        if scale_ratio_range is not None or translation_range is not None:
+            raise NotImplementedError("GlobalRotScaleTrans: only the rotation-only form (pn_rot.py) is supported")
+        if rot_axis not in ("z", 2):
+            raise NotImplementedError("GlobalRotScaleTrans: only rot_axis='z'")
+        if not isinstance(rot_range, (list, tuple)):
+            rot_range = [-rot_range, rot_range]
+        self.rot_range = [float(rot_range[0]), float(rot_range[1])]
+
+    def params(self):
+        return self.kind, self.rot_range[0], self.rot_range[1]
+
+    def __call__(self, data):
+        data = dict(data)
+        ang = None
+        for key in self.req_keys:
+            if key in data:
+                x = data[key]
+                if ang is None:
+                    ang = torch.empty(x.shape[0], device=x.device).uniform_(*self.rot_range)
+                c, s = torch.cos(ang)[:, None], torch.sin(ang)[:, None]
+                data[key] = torch.stack([c * x[:, 0] - s * x[:, 1], s * x[:, 0] + c * x[:, 1], x[:, 2]], dim=1)
+        return data
+
+    def __repr__(self):
+        return f"GlobalRotScaleTrans(rot_range={self.rot_range})"
+
+
+class DataAugmentations:
+    def __init__(self, transforms):
+        self.transforms = [build_from_cfg(t, AUGMENTATIONS) if isinstance(t, dict) else t for t in transforms]
+
+    def __call__(self, data):
+        for t in self.transforms:
+            data = t(data)
+        return data
+
+    def __getitem__(self, i):
+        return self.transforms[i]
+
+    def __len__(self):
+        return len(self.transforms)
+
+
+def build_data_augmentations(cfg, default_args=None):
+    if cfg is None:
+        return None
+    return DataAugmentations(cfg if isinstance(cfg, (list, tuple)) else [cfg])

@@ -1,0 +1,45 @@
+"""C-ABI checks that need no GPU: the shared library loads and exports every symbol include/pcrl.h declares."""
+import ctypes
+import os
+
+from pointcloud_rl_b200._lib import HEADER, LIB_PATH, lib, parse_header
+
+
+def test_header_declares_expected_entry_points():
+    protos = parse_header(HEADER)
+    for name in ("pcrl_stage_points", "pcrl_pointnet_fwd_f32", "pcrl_pointnet_fwd_bf16", "pcrl_pointnet_pack_weights",
+                 "pcrl_pointnet_bwd", "pcrl_linear_fwd", "pcrl_linear_bwd", "pcrl_layernorm_fwd", "pcrl_layernorm_bwd",
+                 "pcrl_tanh_gaussian_fwd", "pcrl_tanh_gaussian_bwd", "pcrl_td_target", "pcrl_critic_loss",
+                 "pcrl_actor_loss", "pcrl_adam_step", "pcrl_polyak"):
+        assert name in protos, name
+    # plain-C signatures only: pointers, fixed-width ints, floats
+    for name, (_, args) in protos.items():
+        for ctype, _ in args:
+            assert ctype in (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint32,
+                             ctypes.c_int32, ctypes.c_float), (name, ctype)
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(LIB_PATH), "build with `python -m pointcloud_rl_b200.build`"
+    L = lib()  # binds every prototype; AttributeError if a symbol is missing
+    assert L.cdll.pcrl_abi_version() == 1
+    assert isinstance(L.last_error(), str)
+    # pure-host queries work without a GPU
+    assert L.pointnet_wpack_bytes(128, 128, 256) == 128 * 32 + 128 * 128 * 2 + 256 * 128 * 2 + (256 + 512) * 4
+    assert L.pointnet_fwd_f32_workspace(2, 1280, 128, 128, 256) == 2 * 1280 * 512 * 4
+    assert L.pointnet_bwd_workspace(4, 256, 128, 128, 256, 8) > 0
+
+
+def test_sass_uses_blackwell_tensor_and_tma_paths():
+    """The shipped cubin must contain tcgen05 MMA (UTC*MMA), TMEM loads (LDTM) and bulk-TMA copies (UBLKCP)."""
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        import pytest
+
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass and "LDTM" in sass and "UBLKCP" in sass
+    assert "sm_100a" in subprocess.run([cuobjdump, "-lelf", LIB_PATH], capture_output=True, text=True).stdout

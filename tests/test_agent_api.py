@@ -1,0 +1,149 @@
+"""The drop-in boundary: agents built through the registry from the package's config files expose the
+reference's module tree / state_dict keys (CPU), and `update_parameters(memory, updates)` reproduces the
+reference's returned dict and weights (GPU, golden vectors)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from pointcloud_rl_b200 import Config, config_path, get_kwargs_from_shape, replace_placeholder_with_args
+from tests.conftest import GOLDEN, load_golden
+
+
+class Box:  # gym.spaces.Box stand-in: the actor only reads low/high/is_bounded (actor_critic.py:69-71)
+    def __init__(self, low, high, shape):
+        self.low, self.high, self.shape = np.full(shape, low, np.float32), np.full(shape, high, np.float32), shape
+
+    def is_bounded(self):
+        return True
+
+
+def make_agent(rel, obs_shape, A, hidden=None, **overrides):
+    from pointcloud_rl_b200.agents import build_agent
+
+    cfg = Config.fromfile(config_path(rel))
+    if hidden:
+        D = cfg.agent_cfg.actor_cfg.nn_cfg.visual_nn_cfg.out_channels
+        state = " + agent_shape" if "agent" in obs_shape else ""
+        cfg.agent_cfg.actor_cfg.nn_cfg.mlp_cfg.mlp_spec = [f"{D}{state}", hidden, hidden, "action_shape * 2"]
+        cfg.agent_cfg.critic_cfg.nn_cfg.mlp_cfg.mlp_spec = [f"{D}{state} + action_shape", hidden, hidden, 1]
+    cfg.merge_from_dict({f"agent_cfg.{k}": v for k, v in overrides.items()})
+    cfg.agent_cfg["env_params"] = dict(obs_shape=obs_shape, action_shape=A, action_space=Box(-1.0, 1.0, (A,)), is_discrete=False)
+    cfg = replace_placeholder_with_args(cfg, **get_kwargs_from_shape(obs_shape, A))
+    return build_agent(cfg.agent_cfg)
+
+
+def test_state_dict_keys_match_reference():
+    obs_shape = {"xyz": [3, 64], "rgb": [3, 64], "seg": [1, 64], "agent": 13}
+    agent = make_agent("mfrl/drq/maniskill/pn_jitter.py", obs_shape, 5, batch_size=4)
+    ours = {k: tuple(v.shape) for k, v in agent.state_dict().items()}
+    ref = {k: tuple(v) for k, v in json.load(open(os.path.join(GOLDEN, "state_dict_keys_drq_maniskill.json"))).items()}
+    assert ours == ref
+    # object identity of the shared backbone (builder.py:28-45,60-66)
+    pn = agent.actor.backbone.visual_nn
+    assert all(v.backbone.visual_nn is pn for v in agent.critic.values)
+    assert all(v.backbone.visual_nn is pn for v in agent.target_critic.values)
+    assert agent.target_entropy == -5 and abs(agent.alpha - 0.1) < 1e-6
+    assert agent.num_aug == 2 and agent._aug == ("jitter", -0.01, 0.01)
+    assert agent.critic.num_trainable_parameters == sum(p.numel() for p in set(agent.critic.parameters()))
+
+
+def test_unsupported_options_raise():
+    obs_shape = {"xyz": [3, 64], "rgb": [3, 64]}
+    with pytest.raises(NotImplementedError):
+        make_agent("mfrl/sac/dm_control/pn.py", obs_shape, 6, shared_backbone=False)
+    from pointcloud_rl_b200.networks import build_all
+
+    with pytest.raises(NotImplementedError):
+        build_all(dict(type="PointNet", feat_dim=6, mlp_spec=[64, 128, 256], out_channels=50, feature_transform=[1]))
+    from pointcloud_rl_b200.augmentations import build_data_augmentations
+
+    with pytest.raises(NotImplementedError):
+        build_data_augmentations(dict(type="GlobalRotScaleTrans", main_key="xyz", req_keys=["xyz"], rot_range=None,
+                                      scale_ratio_range=None, translation_range=[0.1, 0.1, 0.1], shift_height=True))
+
+
+def test_update_needs_cuda_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    from pointcloud_rl_b200.data import FixedBatchMemory
+    from pointcloud_rl_b200.synthetic import synthetic_batch
+
+    agent = make_agent("mfrl/sac/dm_control/pn.py", {"xyz": [3, 32], "rgb": [3, 32]}, 6, hidden=32, batch_size=2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        agent.update_parameters(FixedBatchMemory(synthetic_batch(0, 2, 32, 6)), 1)
+
+
+# ------------------------------------------------------------------------------------------ GPU
+def _load_golden_into(agent, init):
+    from oracle.pointnet_sac_oracle import reference_key_map
+
+    sd = agent.state_dict()
+    for ours, ref in reference_key_map().items():
+        t = torch.from_numpy(np.asarray(init[ours]))
+        sd[ref] = t.reshape(sd[ref].shape)
+    for h in (0, 1):  # the critic heads' backbones alias the actor's: fill the duplicate keys too
+        for k in list(sd):
+            if k.startswith("actor.backbone.visual_nn."):
+                for pre in (f"critic.values.{h}", f"target_critic.values.{h}"):
+                    sd[k.replace("actor", pre, 1)] = sd[k]
+    agent.load_state_dict(sd)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,rel", [("sac_dmc_small", "mfrl/sac/dm_control/pn.py"),
+                                      ("drq_jitter_small", "mfrl/drq/maniskill/pn_jitter.py")])
+def test_update_parameters_through_registry(name, rel):
+    from pointcloud_rl_b200.data import FixedBatchMemory
+
+    g = load_golden(name)
+    m = {k: v.item() for k, v in g["meta"].items()}
+    batch = {k: (dict(v) if isinstance(v, dict) else v) for k, v in g["batch"].items()}
+    obs_shape = {k: (list(v.shape[1:]) if v.ndim > 2 else int(v.shape[1])) for k, v in batch["obs"].items()}
+    agent = make_agent(rel, obs_shape, m["A"], hidden=64, batch_size=m["B"], precision="fp32", use_cuda_graph=False).to("cuda")
+    _load_golden_into(agent, g["init"])
+    eng = agent._ensure_engine(batch)
+    mem = FixedBatchMemory(batch)
+    for u in (1, 2):
+        noise = {k: torch.from_numpy(v).cuda() for k, v in g[f"noise{u}"].items()}
+        # the public call draws its own (Philox) randomness; parity needs the reference's draws injected
+        eng.upload_batch(batch)
+        eng.update(u, noise)
+        ret = eng.read_scalars(u)
+        ref = {f"{a}/{b}": float(v) for a, sub in g[f"ret{u}"].items() for b, v in sub.items()}
+        assert set(ret) == set(ref)
+        for key, val in ref.items():
+            assert ret[key] == pytest.approx(val, rel=1e-3, abs=1e-4), (u, key)
+    # module parameters alias the engine's flat buffer: the nn.Module view moved with the fused Adam
+    w_mod = agent.actor.backbone.visual_nn.conv.mlp.conv1.weight
+    assert w_mod.data_ptr() == eng.p["pn.w1"].data_ptr()
+    assert torch.allclose(w_mod[..., 0].cpu(), torch.from_numpy(g["after2"]["pn.w1"]), atol=1e-4)
+    # and the public call itself (own randomness) returns the reference's keys with finite values
+    out = agent.update_parameters(mem, 4)
+    assert set(out) == set(ref) and all(np.isfinite(v) for v in out.values())
+
+
+@pytest.mark.gpu
+def test_rollout_forward_and_modes():
+    obs_shape = {"xyz": [3, 200], "rgb": [3, 200], "seg": [1, 200], "agent": 13}
+    agent = make_agent("mfrl/drq/maniskill/pn_jitter.py", obs_shape, 5, hidden=64, batch_size=4, precision="fp32").to("cuda")
+    from oracle import pointnet_sac_oracle as O
+
+    rs = np.random.RandomState(0)
+    obs = O.synthetic_obs(rs, 3, 200, n_seg=1, state_dim=13)
+    mean = agent(obs, mode="eval")
+    assert mean.shape == (3, 5) and float(mean.abs().max()) <= 1.0
+    a, nlp = agent(obs, mode="max-entropy")
+    assert a.shape == (3, 5) and nlp.shape == (3, 1)
+    # against the oracle with the agent's own weights
+    sd = {k: v.detach().cpu() for k, v in agent.state_dict().items()}
+    p = O.params_from_reference_state_dict(sd)
+    x = O.preprocess({k: torch.from_numpy(v) for k, v in obs.items() if k != "agent"})
+    f = O.pointnet_forward(p, x)
+    out = O.mlp3(p, "actor", torch.cat([f, torch.from_numpy(obs["agent"])], -1))
+    ref_mean = torch.tanh(out[:, :5])
+    assert torch.allclose(mean.cpu(), ref_mean, atol=1e-4)
+    feat = agent.actor.backbone.visual_nn({k: v for k, v in obs.items() if k != "agent"})
+    assert torch.allclose(feat.cpu(), f, atol=1e-4)

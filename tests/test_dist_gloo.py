@@ -1,0 +1,57 @@
+"""Data-parallel host logic on CPU: world_size-2 gloo run of the gradient all-reduce hook (dist.attach)
+and of the 'sum then scale by 1/world inside Adam' convention the engine uses."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+class _FakeEngine:
+    """The attributes dist.attach touches on UpdateEngine."""
+
+    def __init__(self):
+        self.world_size = 1
+        self.allreduce = None
+        self.params = torch.zeros(8)
+
+    def refresh_alpha(self):
+        pass
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pointcloud_rl_b200.dist import attach, broadcast_params
+
+    eng = attach(_FakeEngine())
+    assert eng.world_size == world and eng.allreduce is not None
+    # each rank's gradient is a mean over its own equal-sized shard; sum * (1/world) == global mean
+    torch.manual_seed(0)
+    per_sample = torch.randn(world * 4, 6)
+    local = per_sample[rank * 4:(rank + 1) * 4].mean(0)
+    flat = local.clone()
+    eng.allreduce(flat)
+    scaled = flat * (1.0 / eng.world_size)
+    ok = torch.allclose(scaled, per_sample.mean(0), atol=1e-6)
+    eng.params = torch.full((8,), float(rank + 1))
+    broadcast_params(eng, src=0)
+    ok = ok and bool((eng.params == 1.0).all())
+    if rank == 0:
+        out.put(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 500
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True
