@@ -105,7 +105,8 @@ int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, cons
                       const int32_t* argmax, const float* dpooled, const float* w0, const float* b0, const float* w1,
                       const float* g1, const float* be1, const float* w2, const float* g2, const float* be2, int c1,
                       int c2, int c3, float ln_eps, float* dw0, float* db0, float* dw1, float* dg1, float* dbe1,
-                      float* dw2, float* dg2, float* dbe2, void* workspace, int64_t workspace_bytes, void* stream);
+                      float* dw2, float* dg2, float* dbe2, void* workspace, int64_t workspace_bytes, int tf32,
+                      void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (4) Dense layers.  y = act(x W^T + b): nn.Linear (+ReLU) of LinearMLP (mlp.py:85-100) and
@@ -116,9 +117,18 @@ int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, cons
  *   (dx row stride lddx).
  * ------------------------------------------------------------------------------------------- */
 int pcrl_linear_fwd(const float* x, int ldx, const float* w, const float* b, float* y, int ldy, int M, int K,
-                    int Nout, int relu, void* stream);
+                    int Nout, int relu, int tf32, void* stream);
 int pcrl_linear_bwd(const float* x, int ldx, const float* w, const float* dy, int lddy, float* dw, float* db,
-                    float* dx, int lddx, int M, int K, int Nout, void* stream);
+                    float* dx, int lddx, int M, int K, int Nout, int tf32, void* stream);
+/* tf32 != 0: run the GEMMs on the tcgen05 TF32 tensor-core kernel (TMA-fed, fp32 inputs consumed as TF32)
+ * whenever the operands meet TMA's alignment rules (16-byte base, row pitch % 4 == 0), else and for
+ * tf32 == 0 the exact-fp32 FFMA kernel runs.
+ *
+ * The raw tensor-core GEMM (tests / microbenchmarks): C[i][j] (op)= sum_l A(i,l) B(l,j) (+bias[j]) (ReLU);
+ * a_mn == 0: A[i*lda+l], a_mn == 1: A[l*lda+i]; b_mn == 0: B[j*ldb+l], b_mn == 1: B[l*ldb+j];
+ * mode 0 store, 1 accumulate, 2 atomic accumulate (required for split_k > 1). */
+int pcrl_gemm_tf32(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, const float* bias, float* C,
+                   int ldc, int M, int N, int K, int relu, int mode, int split_k, void* stream);
 /* dy *= (y > 0) in place: ReLU backward on the saved post-activation */
 int pcrl_relu_bwd(float* dy, const float* y, int64_t n, void* stream);
 /* out[m,j] = a[m,j] + b[m,j] for j < width (summing the two Q heads' input gradients) */

@@ -159,6 +159,7 @@ class SAC(BaseAgent):
         critic_cfg.update(env_params)
         self.env_params = env_params
         self.actor, self.critic = build_actor_critic(actor_cfg, critic_cfg, shared_backbone)
+        self.actor.backbone.visual_nn.precision = precision  # rollout-path encodes use the agent's precision
         shared_target = shared_backbone if shared_target_backbone is None else shared_target_backbone
         self.target_critic = build_target_network(critic_cfg, self.critic, self.actor, shared_target)
 
@@ -235,8 +236,6 @@ class SAC(BaseAgent):
         views = self._named_views()
         eng.load_params(views)
         # re-point every module parameter at the engine's flat buffer (shared storage from here on)
-        for name, prm in views.items():
-            flat = eng.p[name]
         for name, (mod_prm, shape) in self._module_params().items():
             mod_prm.data = eng.p[name].view(shape)
         eng.prime_alpha()

@@ -1,6 +1,7 @@
 // Dense layers, LayerNorm, column copies: the small row-wise pieces around the GEMMs.
 #include "common.cuh"
 #include "rowwise.cuh"
+#include "tc_gemm.cuh"
 
 namespace pcrl {
 
@@ -30,6 +31,37 @@ int launch_colsum(const float* x, int64_t ld, int M, int N, const int* rows_dev,
   int gy = (int)std::min<int64_t>(cdiv(M, 64), 256);
   dim3 grid((unsigned)cdiv(N, 32), (unsigned)gy);
   colsum_kernel<<<grid, 256, 0, st>>>(x, ld, M, N, rows_dev, out);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
+
+int launch_gemm(const GemmArgs& g, int tf32, cudaStream_t st) {
+  if (tf32 && (g.a_sl == 1 || g.a_si == 1) && (g.b_sl == 1 || g.b_sj == 1)) {
+    tcg::TcGemmArgs t{};
+    // prefer the K-major reading when both strides are 1 (degenerate K == 1 / M == 1 shapes)
+    t.a_mn = (g.a_sl == 1) ? 0 : 1;
+    t.A = g.A; t.lda = t.a_mn ? g.a_sl : g.a_si;
+    t.b_mn = (g.b_sl == 1) ? 0 : 1;
+    t.B = g.B; t.ldb = t.b_mn ? g.b_sl : g.b_sj;
+    t.bias = g.bias; t.C = g.C; t.ldc = g.ldc; t.M = g.M; t.N = g.N; t.K = g.K; t.relu = g.relu;
+    t.split_k = g.split_k;
+    t.mode = g.accumulate ? (g.split_k > 1 ? 2 : 1) : 0;
+    t.k_dev = g.k_dev; t.m_dev = g.m_dev;
+    if (g.K >= 8 && tcg::tc_gemm_supported(t)) return tcg::launch_tc_gemm(t, st);
+  }
+  return launch_sgemm(g, st);
+}
+
+__global__ void zero_tail_kernel(float* __restrict__ x, int width, const int* __restrict__ count_dev, int cap) {
+  const int c = *count_dev;
+  const int end = min((c + 31) & ~31, cap);
+  const int64_t n = (int64_t)(end - c) * width;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[(int64_t)c * width + i] = 0.f;
+}
+
+int launch_zero_tail(float* x, int width, const int* count_dev, int capacity_rows, cudaStream_t st) {
+  zero_tail_kernel<<<8, 256, 0, st>>>(x, width, count_dev, capacity_rows);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
@@ -65,7 +97,7 @@ using namespace pcrl;
 extern "C" {
 
 int pcrl_linear_fwd(const float* x, int ldx, const float* w, const float* b, float* y, int ldy, int M, int K,
-                    int Nout, int relu, void* stream) {
+                    int Nout, int relu, int tf32, void* stream) {
   PCRL_CHECK_ARG(x && w && y && M >= 0 && K > 0 && Nout > 0 && ldx >= K && ldy >= Nout);
   GemmArgs g{};
   g.A = x; g.a_si = ldx; g.a_sl = 1;
@@ -73,11 +105,11 @@ int pcrl_linear_fwd(const float* x, int ldx, const float* w, const float* b, flo
   g.C = y; g.ldc = ldy;
   g.M = M; g.N = Nout; g.K = K;
   g.bias = b; g.relu = relu; g.accumulate = 0; g.split_k = 1;
-  return launch_sgemm(g, as_stream(stream));
+  return launch_gemm(g, tf32, as_stream(stream));
 }
 
 int pcrl_linear_bwd(const float* x, int ldx, const float* w, const float* dy, int lddy, float* dw, float* db,
-                    float* dx, int lddx, int M, int K, int Nout, void* stream) {
+                    float* dx, int lddx, int M, int K, int Nout, int tf32, void* stream) {
   PCRL_CHECK_ARG(x && w && dy && M >= 0 && K > 0 && Nout > 0);
   cudaStream_t st = as_stream(stream);
   // dw[n][k] += sum_m dy[m][n] * x[m][k]
@@ -88,11 +120,12 @@ int pcrl_linear_bwd(const float* x, int ldx, const float* w, const float* dy, in
   g.M = Nout; g.N = K; g.K = M;
   g.accumulate = 1;
   // enough CTAs to fill the machine: tiles * split_k >= ~2 waves
-  int64_t tiles = cdiv(Nout, 64) * cdiv(K, 64);
-  int split = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(2 * sm_count(), tiles), cdiv(M, 64)));
+  const int tile = tf32 ? 128 : 64;
+  int64_t tiles = cdiv(Nout, tile) * cdiv(K, tile);
+  int split = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv((tf32 ? 1 : 2) * sm_count(), tiles), cdiv(M, tile)));
   g.split_k = split;
   int rc = 0;
-  if (dw && (rc = launch_sgemm(g, st))) return rc;
+  if (dw && (rc = launch_gemm(g, tf32, st))) return rc;
   if (db) {
     rc = launch_colsum(dy, lddy, M, Nout, nullptr, db, st);
     if (rc) return rc;
@@ -105,7 +138,7 @@ int pcrl_linear_bwd(const float* x, int ldx, const float* w, const float* dy, in
     h.C = dx; h.ldc = lddx;
     h.M = M; h.N = K; h.K = Nout;
     h.split_k = 1;
-    rc = launch_sgemm(h, st);
+    rc = launch_gemm(h, tf32, st);
     if (rc) return rc;
   }
   return PCRL_OK;

@@ -154,7 +154,7 @@ __global__ void relu_bwd_rows_kernel(float* __restrict__ dy, const float* __rest
 }
 
 static int gemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias, int relu, float* C, int ldc,
-                   int M, int K, int Nout, const int* m_dev, cudaStream_t st) {
+                   int M, int K, int Nout, const int* m_dev, cudaStream_t st, int tf32 = 0) {
   // C[M,Nout] = act(A[M,K] W[Nout,K]^T + bias)
   GemmArgs g{};
   g.A = A; g.a_si = lda; g.a_sl = 1;
@@ -162,10 +162,10 @@ static int gemm_nt(const float* A, int lda, const float* W, int ldw, const float
   g.C = C; g.ldc = ldc;
   g.M = M; g.N = Nout; g.K = K;
   g.bias = bias; g.relu = relu; g.split_k = 1; g.m_dev = m_dev;
-  return launch_sgemm(g, st);
+  return launch_gemm(g, tf32, st);
 }
 static int gemm_nn(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int K, int Nout,
-                   const int* m_dev, cudaStream_t st) {
+                   const int* m_dev, cudaStream_t st, int tf32 = 0) {
   // C[M,Nout] = A[M,K] W[K,Nout]
   GemmArgs g{};
   g.A = A; g.a_si = lda; g.a_sl = 1;
@@ -173,10 +173,10 @@ static int gemm_nn(const float* A, int lda, const float* W, int ldw, float* C, i
   g.C = C; g.ldc = ldc;
   g.M = M; g.N = Nout; g.K = K;
   g.split_k = 1; g.m_dev = m_dev;
-  return launch_sgemm(g, st);
+  return launch_gemm(g, tf32, st);
 }
 static int gemm_tn_acc(const float* A, int lda, const float* Bm, int ldb, float* C, int ldc, int Mrows, int Na, int Nb,
-                       const int* rows_dev, int expected_rows, cudaStream_t st) {
+                       const int* rows_dev, int expected_rows, cudaStream_t st, int tf32 = 0) {
   // C[Na,Nb] += A[Mrows,Na]^T Bm[Mrows,Nb]   (contraction over rows, split across CTAs)
   GemmArgs g{};
   g.A = A; g.a_si = 1; g.a_sl = lda;
@@ -184,9 +184,10 @@ static int gemm_tn_acc(const float* A, int lda, const float* Bm, int ldb, float*
   g.C = C; g.ldc = ldc;
   g.M = Na; g.N = Nb; g.K = Mrows;
   g.accumulate = 1; g.k_dev = rows_dev;
-  int64_t tiles = cdiv(Na, 64) * cdiv(Nb, 64);
-  g.split_k = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(4 * sm_count(), tiles), cdiv(expected_rows, 128)));
-  return launch_sgemm(g, st);
+  const int tile = tf32 ? 128 : 64;
+  int64_t tiles = cdiv(Na, tile) * cdiv(Nb, tile);
+  g.split_k = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv((tf32 ? 2 : 4) * sm_count(), tiles), cdiv(expected_rows, 128)));
+  return launch_gemm(g, tf32, st);
 }
 
 }  // namespace pcrl
@@ -276,7 +277,8 @@ int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, cons
                       const int32_t* argmax, const float* dpooled, const float* w0, const float* b0, const float* w1,
                       const float* g1, const float* be1, const float* w2, const float* g2, const float* be2, int c1,
                       int c2, int c3, float ln_eps, float* dw0, float* db0, float* dw1, float* dg1, float* dbe1,
-                      float* dw2, float* dg2, float* dbe2, void* workspace, int64_t workspace_bytes, void* stream) {
+                      float* dw2, float* dg2, float* dbe2, void* workspace, int64_t workspace_bytes, int tf32,
+                      void* stream) {
   PCRL_CHECK_ARG(xf && pooled && argmax && dpooled && workspace && dw0 && db0 && dw1 && dg1 && dbe1 && dw2 && dg2 && dbe2);
   PCRL_CHECK_ARG(R >= 0 && NP % 128 == 0 && NP >= N && C <= CP && R <= 1024 * 1024);
   if (R == 0) return PCRL_OK;
@@ -301,10 +303,10 @@ int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, cons
   PCRL_CHECK_LAUNCH();
 
   // 2. recompute the forward of the active points, keeping what LN backward needs
-  if ((rc = gemm_nt(w.xa, CP, w0, C, b0, 1, w.h0, c1, A, C, c1, w.total, st))) return rc;
-  if ((rc = gemm_nt(w.h0, c1, w1, c1, nullptr, 0, w.h1, c2, A, c1, c2, w.total, st))) return rc;
+  if ((rc = gemm_nt(w.xa, CP, w0, C, b0, 1, w.h0, c1, A, C, c1, w.total, st, 0))) return rc;  // K = C is tiny: FFMA
+  if ((rc = gemm_nt(w.h0, c1, w1, c1, nullptr, 0, w.h1, c2, A, c1, c2, w.total, st, tf32))) return rc;
   if ((rc = launch_ln_rows(w.h1, c2, g1, be1, w.h1, c2, w.y1hat, w.rstd1, A, c2, ln_eps, 1, w.total, st))) return rc;
-  if ((rc = gemm_nt(w.h1, c2, w2, c2, nullptr, 0, w.d2, c3, A, c2, c3, w.total, st))) return rc;
+  if ((rc = gemm_nt(w.h1, c2, w2, c2, nullptr, 0, w.d2, c3, A, c2, c3, w.total, st, tf32))) return rc;
   // (the post-LN activation of layer 2 itself is not needed: only xhat2 / rstd2)
   if ((rc = launch_ln_rows(w.d2, c3, g2, be2, w.d2, c3, w.y2hat, w.rstd2, A, c3, ln_eps, 1, w.total, st))) return rc;
 
@@ -316,18 +318,27 @@ int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, cons
 
   // 4. layer 2 backward: LN -> dW2, dh1
   if ((rc = launch_ln_rows_bwd(w.d2, c3, w.y2hat, w.rstd2, g2, dg2, dbe2, w.d2, c3, A, c3, w.total, st))) return rc;
-  if ((rc = gemm_tn_acc(w.d2, c3, w.h1, c2, dw2, c2, A, c3, c2, w.total, expect, st))) return rc;
-  if ((rc = gemm_nn(w.d2, c3, w2, c2, w.d1, c2, A, c3, c2, w.total, st))) return rc;
+  if (tf32) {
+    if ((rc = launch_zero_tail(w.d2, c3, w.total, A, st))) return rc;
+    if ((rc = launch_zero_tail(w.h1, c2, w.total, A, st))) return rc;
+    if ((rc = launch_zero_tail(w.h0, c1, w.total, A, st))) return rc;
+    if ((rc = launch_zero_tail(w.xa, CP, w.total, A, st))) return rc;
+  }
+  if ((rc = gemm_tn_acc(w.d2, c3, w.h1, c2, dw2, c2, A, c3, c2, w.total, expect, st, tf32))) return rc;
+  if ((rc = gemm_nn(w.d2, c3, w2, c2, w.d1, c2, A, c3, c2, w.total, st, tf32))) return rc;
   relu_bwd_rows_kernel<<<sm_count() * 4, 256, 0, st>>>(w.d1, w.h1, c2, w.total);
   PCRL_CHECK_LAUNCH();
   // 5. layer 1 backward
   if ((rc = launch_ln_rows_bwd(w.d1, c2, w.y1hat, w.rstd1, g1, dg1, dbe1, w.d1, c2, A, c2, w.total, st))) return rc;
-  if ((rc = gemm_tn_acc(w.d1, c2, w.h0, c1, dw1, c1, A, c2, c1, w.total, expect, st))) return rc;
-  if ((rc = gemm_nn(w.d1, c2, w1, c1, w.d0, c1, A, c2, c1, w.total, st))) return rc;
+  if (tf32 && (rc = launch_zero_tail(w.d1, c2, w.total, A, st))) return rc;
+  if ((rc = gemm_tn_acc(w.d1, c2, w.h0, c1, dw1, c1, A, c2, c1, w.total, expect, st, tf32))) return rc;
+  if ((rc = gemm_nn(w.d1, c2, w1, c1, w.d0, c1, A, c2, c1, w.total, st, tf32))) return rc;
   relu_bwd_rows_kernel<<<sm_count() * 4, 256, 0, st>>>(w.d0, w.h0, c1, w.total);
   PCRL_CHECK_LAUNCH();
   // 6. layer 0 backward: dW0 [c1,C] += d0^T xa[:, :C];  db0 += colsum(d0)
-  if ((rc = gemm_tn_acc(w.d0, c1, w.xa, CP, dw0, C, A, c1, C, w.total, expect, st))) return rc;
+  if (tf32 && (rc = launch_zero_tail(w.d0, c1, w.total, A, st))) return rc;
+  // layer-0 weight gradient stays on exact-fp32 FFMA: raw coordinates lose too much under TF32 truncation, and N = C is tiny
+  if ((rc = gemm_tn_acc(w.d0, c1, w.xa, CP, dw0, C, A, c1, C, w.total, expect, st, 0))) return rc;
   if ((rc = launch_colsum(w.d0, c1, A, c1, w.total, db0, st))) return rc;
   return PCRL_OK;
 }

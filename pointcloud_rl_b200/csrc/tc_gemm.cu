@@ -1,0 +1,362 @@
+// Generic TF32 GEMM on tcgen05 tensor cores, operands streamed by TMA (tensor maps over the plain
+// row-major fp32 matrices, 128B swizzle), accumulator in TMEM:
+//
+//     C[i][j] (op)= sum_l A(i,l) * B(l,j) (+ bias[j]) (ReLU)
+//
+// A is given either K-major (A[i*lda + l], the forward `x W^T`) or MN-major (A[l*lda + i], the `dY^T X`
+// weight gradient); likewise B (B[j*ldb + l] K-major / B[l*ldb + j] MN-major).  Both majors are native
+// UMMA operand layouts, so the backward GEMMs need no transposed copies.  fp32 inputs are consumed as
+// TF32 directly (no conversion pass).  Used for the actor/critic MLP layers (fwd + bwd) and for the
+// compacted PointNet backward; the exact-fp32 parity path stays on sgemm.cu.
+//
+// One 128 x BN output tile per CTA (optionally a K-split slice of it): warp 0 = TMA producer,
+// warp 1 = MMA issuer, warps 2-5 = epilogue (TMEM -> registers -> bias/ReLU -> global).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tc_gemm.cuh"
+
+namespace pcrl {
+namespace tcg {
+
+constexpr int BM = 128;
+constexpr int BK = 32;  // fp32 elements: one 128-byte swizzle row
+constexpr int kThreads = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptors (version 1 = sm_100)
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;  // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
+  return d;
+}
+// K-major fp32/TF32 tile: 128 B rows, 16 B-granular 128B swizzle, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) { return desc_sw128(saddr, 16, 1024, 2); }
+// MN-major TF32 tile: the only legal layout for 32-bit MN-major operands is the 128B swizzle with a 32 B
+// base (Swizzle<2,5,2>, atoms of 4 contraction rows x 128 B): SBO = 512 B between 4-row groups along K,
+// LBO = bytes between successive 32-element blocks along M/N (one TMA box each).
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr) { return desc_sw128(saddr, 4096, 512, 1); }
+__device__ __forceinline__ uint32_t idesc_tf32(int n, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct Params {
+  float* C;
+  int64_t ldc;
+  const float* bias;
+  int M, N, K;
+  int bn;        // output tile width (16..128, multiple of 16)
+  int a_mn, b_mn;
+  int relu;
+  int mode;      // 0 store, 1 C += (owned tile), 2 atomic add (split-K)
+  int split_k;
+  int stages;
+  const int* k_dev;  // optional device-side bound on the contraction length
+  const int* m_dev;  // optional device-side bound on M
+};
+
+template <int TMEM_COLS>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Params P) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // 1024-byte alignment for the 128B swizzle atoms
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_bytes = BM * BK * 4, b_bytes = (uint32_t)P.bn * BK * 4;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t bar0 = sbase + (uint32_t)P.stages * stage_bytes;  // full[s], empty[s], acc
+  auto FULL = [&](int s) { return bar0 + 8u * s; };
+  auto EMPTY = [&](int s) { return bar0 + 8u * (P.stages + s); };
+  const uint32_t ACC = bar0 + 8u * (2 * P.stages);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + (size_t)P.stages * stage_bytes + 8 * (2 * P.stages + 1));
+
+  const int K = P.k_dev ? min(P.K, *P.k_dev) : P.K;
+  const int kb_total = (K + BK - 1) / BK;
+  const int kb_per = (kb_total + P.split_k - 1) / P.split_k;
+  const int kb0 = blockIdx.z * kb_per;
+  const int kb1 = min(kb_total, kb0 + kb_per);
+  const int nkb = max(kb1 - kb0, 0);
+  const int i0 = blockIdx.y * BM, j0 = blockIdx.x * P.bn;
+  if (P.m_dev && i0 >= *P.m_dev) return;  // whole tile past the device-side row count (before any allocation)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.stages; ++s) {
+      mbar_init(FULL(s), 1);
+      mbar_init(EMPTY(s), 1);
+    }
+    mbar_init(ACC, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32((const void*)tmem_ptr_smem)),
+                 "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int s = kb % P.stages;
+          if (kb >= P.stages) mbar_wait(EMPTY(s), ((kb / P.stages) - 1) & 1);
+          mbar_expect_tx(FULL(s), stage_bytes);
+          const uint32_t sa = sbase + s * stage_bytes, sb = sa + a_bytes;
+          const int l0 = (kb0 + kb) * BK;
+          if (!P.a_mn) {
+            tma_load_2d(sa, &map_a, l0, i0, FULL(s));  // box {32 (K), 128 rows}
+          } else {
+            for (int b = 0; b < BM / 32; ++b) tma_load_2d(sa + b * 4096, &map_a, i0 + b * 32, l0, FULL(s));  // {32 (M), 32 K-rows}
+          }
+          if (!P.b_mn) {
+            tma_load_2d(sb, &map_b, l0, j0, FULL(s));  // box {32 (K), bn rows}
+          } else {
+            for (int b = 0; b < P.bn / 32; ++b) tma_load_2d(sb + b * 4096, &map_b, j0 + b * 32, l0, FULL(s));
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = idesc_tf32(P.bn, P.a_mn, P.b_mn);
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int s = kb % P.stages;
+          mbar_wait(FULL(s), (kb / P.stages) & 1);
+          tc_fence_after();
+          const uint32_t sa = sbase + s * stage_bytes, sb = sa + a_bytes;
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            // K-major: +32 B inside the 128 B swizzle row per 8-element K step; MN-major: next 8-row group
+            const uint64_t ad = P.a_mn ? desc_mnmajor(sa + ks * 1024) : desc_kmajor(sa + ks * 32);
+            const uint64_t bd = P.b_mn ? desc_mnmajor(sb + ks * 1024) : desc_kmajor(sb + ks * 32);
+            mma_tf32(tmem_base, ad, bd, idesc, (kb | ks) != 0);
+          }
+          mma_commit(EMPTY(s));
+        }
+        mma_commit(ACC);
+      }
+    } else {
+      // epilogue: warp (2..5) -> TMEM lane quadrant warp%4
+      const int q = warp & 3;
+      const int row = i0 + q * 32 + lane;
+      mbar_wait(ACC, 0);
+      tc_fence_after();
+      uint32_t v[32];
+      for (int c = 0; c < P.bn; c += 32) {
+        if (c + 32 <= P.bn) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, v);
+        } else {
+          // bn == 16 / 48 / ...: a 16-column tail
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+              : "r"(tmem_base + ((uint32_t)(q * 32) << 16) + c));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
+        const int ncol = min(32, P.bn - c);
+        if (row < P.M) {
+          float* crow = P.C + (int64_t)row * P.ldc + j0 + c;
+          const bool vec_ok = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && (j0 + c + ncol <= P.N);
+#pragma unroll
+          for (int j4 = 0; j4 < 32; j4 += 4) {
+            if (j4 >= ncol) break;
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int col = j0 + c + j4 + e;
+              float x = __uint_as_float(v[j4 + e]);
+              if (P.bias && blockIdx.z == 0 && col < P.N) x += __ldg(P.bias + col);
+              if (P.relu) x = fmaxf(x, 0.f);
+              o[e] = x;
+            }
+            if (P.mode == 0 && vec_ok) {
+              *reinterpret_cast<float4*>(crow + j4) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (j0 + c + j4 + e < P.N) {
+                  if (P.mode == 0) crow[j4 + e] = o[e];
+                  else if (P.mode == 1) crow[j4 + e] += o[e];
+                  else atomicAdd(crow + j4 + e, o[e]);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (P.mode == 0 && blockIdx.z == 0 && warp >= 2) {
+    // empty contraction: C = act(bias)
+    const int row = i0 + (warp & 3) * 32 + lane;
+    if (row < P.M)
+      for (int c = 0; c < P.bn && j0 + c < P.N; ++c) {
+        float x = P.bias ? P.bias[j0 + c] : 0.f;
+        P.C[(int64_t)row * P.ldc + j0 + c] = P.relu ? fmaxf(x, 0.f) : x;
+      }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map: inner dimension `inner` elements (contiguous), `outer` rows of pitch ld elements.
+static bool make_map(CUtensorMap* m, const float* base, int64_t inner, int64_t outer, int64_t ld, int box_inner,
+                     int box_outer, bool mn_major) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+bool tc_gemm_supported(const TcGemmArgs& g) {
+  auto ok = [](const float* p, int64_t ld) { return p && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % 4 == 0 && ld > 0; };
+  if (!ok(g.A, g.lda) || !ok(g.B, g.ldb)) return false;
+  if (g.M < 1 || g.N < 1 || g.K < 1) return false;
+  return get_encode() != nullptr;
+}
+
+int launch_tc_gemm(const TcGemmArgs& g, cudaStream_t st) {
+  if (!tc_gemm_supported(g)) {
+    set_error("tc_gemm: operands must be 16-byte aligned with row pitch %% 4 == 0");
+    return PCRL_EINVAL;
+  }
+  // output tile width: wide tiles when there is enough work, narrower ones to keep >= ~1 wave of CTAs
+  int bn = 128;
+  const int64_t mt = cdiv(g.M, BM);
+  const int sms = sm_count();
+  while (bn > 32 && mt * cdiv(g.N, bn) * g.split_k < sms) bn >>= 1;
+  if (g.N <= 16) bn = 16;
+  else if (g.N <= 32) bn = 32;
+  else if (g.N <= 64 && bn > 64) bn = 64;
+  if (g.b_mn && bn < 32) bn = 32;  // MN-major B is loaded in 32-column boxes
+  Params P{};
+  P.C = g.C; P.ldc = g.ldc; P.bias = g.bias; P.M = g.M; P.N = g.N; P.K = g.K; P.bn = bn; P.a_mn = g.a_mn; P.b_mn = g.b_mn;
+  P.relu = g.relu; P.mode = g.mode; P.split_k = g.split_k; P.k_dev = g.k_dev; P.m_dev = g.m_dev;
+  PCRL_CHECK_ARG(g.split_k >= 1 && (g.split_k == 1 || (g.mode == 2 && !g.relu)));
+  const uint32_t stage_bytes = BM * BK * 4 + bn * BK * 4;
+  P.stages = (int)std::min<int64_t>(6, std::max<int64_t>(2, (200 * 1024) / stage_bytes));
+  const size_t smem = (size_t)P.stages * stage_bytes + 8 * (2 * P.stages + 2) + 16 + 1024;
+
+  CUtensorMap ma, mb;
+  bool okm;
+  if (!g.a_mn) okm = make_map(&ma, g.A, g.K, g.M, g.lda, BK, BM, false);        // A[i*lda + l]
+  else         okm = make_map(&ma, g.A, g.M, g.K, g.lda, 32, BK, true);        // A[l*lda + i]
+  if (!g.b_mn) okm = okm && make_map(&mb, g.B, g.K, g.N, g.ldb, BK, bn, false); // B[j*ldb + l]
+  else         okm = okm && make_map(&mb, g.B, g.N, g.K, g.ldb, 32, BK, true); // B[l*ldb + j]
+  if (!okm) {
+    set_error("tc_gemm: cuTensorMapEncodeTiled failed");
+    return PCRL_ECUDA;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    PCRL_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)cdiv(g.N, bn), (unsigned)mt, (unsigned)g.split_k);
+  tc_gemm_kernel<128><<<grid, kThreads, smem, st>>>(ma, mb, P);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
+
+}  // namespace tcg
+}  // namespace pcrl
+
+using namespace pcrl;
+
+// Test / benchmark hook for the raw GEMM: C = act(op(A) op(B) + bias), see include/pcrl.h
+extern "C" int pcrl_gemm_tf32(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, const float* bias,
+                              float* C, int ldc, int M, int N, int K, int relu, int mode, int split_k, void* stream) {
+  PCRL_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0);
+  tcg::TcGemmArgs g{};
+  g.A = A; g.lda = lda; g.a_mn = a_mn; g.B = B; g.ldb = ldb; g.b_mn = b_mn; g.bias = bias; g.C = C; g.ldc = ldc;
+  g.M = M; g.N = N; g.K = K; g.relu = relu; g.mode = mode; g.split_k = split_k;
+  return tcg::launch_tc_gemm(g, as_stream(stream));
+}

@@ -151,6 +151,9 @@ class UpdateEngine:
         self.R = self.B * self.k
         self.device = torch.device(device)
         self.precision = precision
+        # "bf16" = the fast mode: bf16 tcgen05 PointNet forward + TF32 tcgen05 GEMMs for the MLP heads and the
+        # compacted backward; "fp32" = the parity mode: every product on the exact-fp32 FFMA kernels
+        self.tf32 = 1 if precision == "bf16" else 0
         self.seed = int(seed)
         self.layout = ParamLayout(spec)
         dev = self.device
@@ -319,7 +322,7 @@ class UpdateEngine:
                                     c3, sp.ln_eps, w[f"pooled_{name}"], argmax, w["scratch"], self.fwd_ws_bytes, st)
         D = sp.out_dim
         cat = w[f"cat_{name}"]
-        self.L.linear_fwd(w[f"pooled_{name}"], c3, p["pn.wf"], p["pn.bf"], w[f"z_{name}"], D, rows, c3, D, 0, st)
+        self.L.linear_fwd(w[f"pooled_{name}"], c3, p["pn.wf"], p["pn.bf"], w[f"z_{name}"], D, rows, c3, D, 0, self.tf32, st)
         save = want_argmax
         self.L.layernorm_fwd(w[f"z_{name}"], p["pn.gf"], p["pn.bef"], cat, cat.stride(0),
                              w["xhat_obs"] if save else None, w["rstd_obs"] if save else None, rows, D,
@@ -339,20 +342,20 @@ class UpdateEngine:
         p, (h1n, h2n) = self.p, self.spec.hidden
         h1, h2 = self.w[f"h1_{keep}"], self.w[f"h2_{keep}"]
         ldx = x.stride(0)
-        self.L.linear_fwd(x, ldx, p[f"{net}.w0"], p[f"{net}.b0"], h1, h1n, M, K, h1n, 1, st)
-        self.L.linear_fwd(h1, h1n, p[f"{net}.w1"], p[f"{net}.b1"], h2, h2n, M, h1n, h2n, 1, st)
-        self.L.linear_fwd(h2, h2n, p[f"{net}.w2"], p[f"{net}.b2"], out, ldo, M, h2n, nout, 0, st)
+        self.L.linear_fwd(x, ldx, p[f"{net}.w0"], p[f"{net}.b0"], h1, h1n, M, K, h1n, 1, self.tf32, st)
+        self.L.linear_fwd(h1, h1n, p[f"{net}.w1"], p[f"{net}.b1"], h2, h2n, M, h1n, h2n, 1, self.tf32, st)
+        self.L.linear_fwd(h2, h2n, p[f"{net}.w2"], p[f"{net}.b2"], out, ldo, M, h2n, nout, 0, self.tf32, st)
 
     def _mlp_bwd(self, net, x, K, M, dout, lddo, nout, keep, dx, want_w, st):
         p, g, w, (h1n, h2n) = self.p, self.g, self.w, self.spec.hidden
         h1, h2 = w[f"h1_{keep}"], w[f"h2_{keep}"]
         gw = (lambda n: g[f"{net}.{n}"]) if want_w else (lambda n: None)
-        self.L.linear_bwd(h2, h2n, p[f"{net}.w2"], dout, lddo, gw("w2"), gw("b2"), w["dh2"], h2n, M, h2n, nout, st)
+        self.L.linear_bwd(h2, h2n, p[f"{net}.w2"], dout, lddo, gw("w2"), gw("b2"), w["dh2"], h2n, M, h2n, nout, self.tf32, st)
         self.L.relu_bwd(w["dh2"], h2, M * h2n, st)
-        self.L.linear_bwd(h1, h1n, p[f"{net}.w1"], w["dh2"], h2n, gw("w1"), gw("b1"), w["dh1"], h1n, M, h1n, h2n, st)
+        self.L.linear_bwd(h1, h1n, p[f"{net}.w1"], w["dh2"], h2n, gw("w1"), gw("b1"), w["dh1"], h1n, M, h1n, h2n, self.tf32, st)
         self.L.relu_bwd(w["dh1"], h1, M * h1n, st)
         self.L.linear_bwd(x, x.stride(0), p[f"{net}.w0"], w["dh1"], h1n, gw("w0"), gw("b0"), dx,
-                          dx.stride(0) if dx is not None else 0, M, K, h1n, st)
+                          dx.stride(0) if dx is not None else 0, M, K, h1n, self.tf32, st)
 
     def _adam(self, group, idx, lr, betas, gradsq_slot, polyak, st):
         lo, hi = self.layout.group_range[group]
@@ -420,12 +423,12 @@ class UpdateEngine:
         L.layernorm_bwd(w["dz"], D, w["xhat_obs"], w["rstd_obs"], p["pn.gf"], self.g["pn.gf"], self.g["pn.bef"],
                         w["dz"], R, D, st)
         L.linear_bwd(w["pooled_obs"], c3, p["pn.wf"], w["dz"], D, self.g["pn.wf"], self.g["pn.bf"], w["dpooled"], c3,
-                     R, c3, D, st)
+                     R, c3, D, self.tf32, st)
         g = self.g
         L.pointnet_bwd(w["xf_obs"], R, sp.n_points, sp.NP, sp.CP, sp.C, w["pooled_obs"], w["argmax_obs"], w["dpooled"],
                        p["pn.w0"], p["pn.b0"], p["pn.w1"], p["pn.g1"], p["pn.be1"], p["pn.w2"], p["pn.g2"],
                        p["pn.be2"], c1, c2, c3, sp.ln_eps, g["pn.w0"], g["pn.b0"], g["pn.w1"], g["pn.g1"], g["pn.be1"],
-                       g["pn.w2"], g["pn.g2"], g["pn.be2"], w["scratch"], self.bwd_ws_bytes, st)
+                       g["pn.w2"], g["pn.g2"], g["pn.be2"], w["scratch"], self.bwd_ws_bytes, self.tf32, st)
         if self.allreduce is not None:
             self.allreduce(self.grads[c_lo:c_hi])
         self._adam("critic", 0, hp.lr, hp.betas, 4, do_target, st)  # + Polyak fused (sac.py:207-208)

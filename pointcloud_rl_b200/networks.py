@@ -159,6 +159,7 @@ class KernelRunner:
 
     def __init__(self, precision="bf16", seed=0):
         self.precision = precision
+        self.tf32 = 1 if precision == "bf16" else 0
         self.seed = seed
         self._ws = {}
         self._counter = None
@@ -221,7 +222,7 @@ class KernelRunner:
         D = spec.out_dim
         if out is None:
             out = torch.empty(B, D, dtype=torch.float32, device=device)
-        L.linear_fwd(ws["pooled"], c3, p["pn.wf"], p["pn.bf"], ws["z"], D, B, c3, D, 0, st)
+        L.linear_fwd(ws["pooled"], c3, p["pn.wf"], p["pn.bf"], ws["z"], D, B, c3, D, 0, self.tf32, st)
         L.layernorm_fwd(ws["z"], p["pn.gf"], p["pn.bef"], out, out.stride(0), None, None, B, D, spec.head_ln_eps, st)
         self.calls += 1
         return out
@@ -233,9 +234,9 @@ class KernelRunner:
         h1 = torch.empty(M, h1n, dtype=torch.float32, device=dev)
         h2 = torch.empty(M, h2n, dtype=torch.float32, device=dev)
         out = torch.empty(M, nout, dtype=torch.float32, device=dev)
-        L.linear_fwd(x, x.stride(0), p[f"{net}.w0"], p[f"{net}.b0"], h1, h1n, M, K, h1n, 1, st)
-        L.linear_fwd(h1, h1n, p[f"{net}.w1"], p[f"{net}.b1"], h2, h2n, M, h1n, h2n, 1, st)
-        L.linear_fwd(h2, h2n, p[f"{net}.w2"], p[f"{net}.b2"], out, nout, M, h2n, nout, 0, st)
+        L.linear_fwd(x, x.stride(0), p[f"{net}.w0"], p[f"{net}.b0"], h1, h1n, M, K, h1n, 1, self.tf32, st)
+        L.linear_fwd(h1, h1n, p[f"{net}.w1"], p[f"{net}.b1"], h2, h2n, M, h1n, h2n, 1, self.tf32, st)
+        L.linear_fwd(h2, h2n, p[f"{net}.w2"], p[f"{net}.b2"], out, nout, M, h2n, nout, 0, self.tf32, st)
         return out
 
 
