@@ -227,6 +227,18 @@ def native_arm(args, w, rank, world, local_rank):
         step_fn(u)
     barrier()
 
+    if args.profile_window:
+        # `ncu --profile-from-start off ...`: exactly two updates (one critic-only, one with the actor/alpha/Polyak
+        # branches) inside the cudaProfilerStart/Stop window, launched eagerly so every kernel is visible
+        torch.cuda.profiler.start()
+        eng.update(1)
+        eng.update(2)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---- device-resident throughput (`value`)
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -336,6 +348,7 @@ def main():
     ap.add_argument("--workload", default="drq_maniskill_pn_jitter", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-window", action="store_true", help="run 2 eager updates inside cudaProfilerStart/Stop and exit")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", 0))

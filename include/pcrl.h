@@ -13,7 +13,8 @@
  *   - return value: 0 = ok, otherwise a PCRL_E* code; pcrl_last_error() gives a message
  *   - row-major fp32 everywhere unless stated otherwise
  *   - R = clouds (batch rows after augmentation), N = points per cloud, NP = N rounded up to a
- *     multiple of 128 (padding points are zero and never win the max-pool), CP = channels padded to 8 or 16
+ *     multiple of 128 (padding rows replicate the cloud's point 0, so they tie with it and the
+ *     smallest-index rule keeps them out of the argmax), CP = channels padded to 8 or 16
  */
 #ifndef PCRL_H_
 #define PCRL_H_

@@ -44,12 +44,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(bar),
       "r"(parity)
       : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -87,6 +98,18 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -104,6 +127,19 @@ __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
   uint32_t d;
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
+}
+
+// sum and sum of squares of one 32-column chunk, 4 independent dependency chains
+__device__ __forceinline__ void stats32(const uint32_t (&v)[32], float (&s)[4], float (&q)[4]) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float y = __uint_as_float(v[j + e]);
+      s[e] += y;
+      q[e] = fmaf(y, y, q[e]);
+    }
+  }
 }
 
 struct SmemLayout {
@@ -188,41 +224,49 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       mbar_wait(BAR(0), 0);
-      uint32_t ph_act[2] = {0, 0};
       const uint32_t id0 = make_idesc(c1), id1 = make_idesc(c2), id2 = make_idesc(c3);
       const int kmax = c1 > c2 ? c1 : c2;
-      for (int p = 0; 2 * p < n_local; ++p) {
-#pragma unroll 1
-        for (int layer = 0; layer < 3; ++layer) {
-#pragma unroll 1
-          for (int s = 0; s < 2; ++s) {
-            const int i = 2 * p + s;
-            if (i >= n_local) continue;
-            const uint32_t d_tmem = tmem_base + (uint32_t)(s * 256);
-            const uint32_t act = sbase + L.act + (uint32_t)(s * 128 * kmax * 2);
-            if (layer == 0) {
-              const int st = i % kStages;
-              mbar_wait(BAR(1 + st), (i / kStages) & 1);
-              if (p > 0) {  // previous tile's layer-2 accumulator must be drained
-                mbar_wait(BAR(11 + s), ph_act[s] & 1);
-                ph_act[s]++;
-              }
-              tc_fence_after();
-              mma_bf16(d_tmem, make_desc(sbase + L.xst + st * kTileBytes, 256), make_desc(sbase + L.w0, 256), id0, 0);
-              mma_commit(BAR(5 + st));
-            } else {
-              mbar_wait(BAR(11 + s), ph_act[s] & 1);
-              ph_act[s]++;
-              tc_fence_after();
-              const int K = (layer == 1) ? c1 : c2;
-              const uint32_t wb = sbase + ((layer == 1) ? L.w1 : L.w2);
-              const uint32_t idesc = (layer == 1) ? id1 : id2;
-              for (int ks = 0; ks < K / 16; ++ks)
-                mma_bf16(d_tmem, make_desc(act + ks * 256, K * 16), make_desc(wb + ks * 256, K * 16), idesc, ks > 0);
-            }
-            mma_commit(BAR(9 + s));
+      // per-slot progress: tile index (s, s+2, ...), layer, and how many epilogue hand-offs were consumed.
+      // The issuer polls both slots and launches whichever is ready, so a slow epilogue on one slot never
+      // holds back the other slot's next layer.
+      int tile_i[2] = {0, 1}, layer[2] = {0, 0};
+      uint32_t ph_act[2] = {0, 0};
+      bool first[2] = {true, true};
+      while (tile_i[0] < n_local || tile_i[1] < n_local) {
+        bool progressed = false;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int i = tile_i[s];
+          if (i >= n_local) continue;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(s * 256);
+          const uint32_t act = sbase + L.act + (uint32_t)(s * 128 * kmax * 2);
+          if (layer[s] == 0) {
+            const int st = i % kStages;
+            if (!mbar_test(BAR(1 + st), (i / kStages) & 1)) continue;                  // point tile landed?
+            if (!first[s] && !mbar_test(BAR(11 + s), ph_act[s] & 1)) continue;         // previous layer-2 accumulator drained?
+            if (!first[s]) ph_act[s]++;
+            first[s] = false;
+            tc_fence_after();
+            mma_bf16(d_tmem, make_desc(sbase + L.xst + st * kTileBytes, 256), make_desc(sbase + L.w0, 256), id0, 0);
+            mma_commit(BAR(5 + st));
+          } else {
+            if (!mbar_test(BAR(11 + s), ph_act[s] & 1)) continue;                      // h_{layer-1} written?
+            ph_act[s]++;
+            tc_fence_after();
+            const int K = (layer[s] == 1) ? c1 : c2;
+            const uint32_t wb = sbase + ((layer[s] == 1) ? L.w1 : L.w2);
+            const uint32_t idesc = (layer[s] == 1) ? id1 : id2;
+            for (int ks = 0; ks < K / 16; ++ks)
+              mma_bf16(d_tmem, make_desc(act + ks * 256, K * 16), make_desc(wb + ks * 256, K * 16), idesc, ks > 0);
+          }
+          mma_commit(BAR(9 + s));
+          progressed = true;
+          if (++layer[s] == 3) {
+            layer[s] = 0;
+            tile_i[s] += 2;
           }
         }
+        if (!progressed) __nanosleep(40);
       }
     }
   } else {
@@ -244,8 +288,7 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
     for (int i = s; i < n_local; i += 2) {
       const int64_t tile = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
       const int cloud = (int)(tile / tiles_per_cloud);
-      const int n_in_cloud = (int)(tile % tiles_per_cloud) * 128 + row;
-      uint32_t v[32];
+      uint32_t v[32], v2[32];
 
       // ---- layer 0: relu -> bf16 -> activation buffer (K = c1)
       mbar_wait(BAR(9 + s), ph_acc & 1);
@@ -276,16 +319,17 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
       ph_acc++;
       tc_fence_after();
       {
-        float sum = 0.f, sq = 0.f;
-        for (int ch = 0; ch < c2; ch += 32) {
-          tmem_ld32(taddr0 + ch, v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float y = __uint_as_float(v[j]);
-            sum += y;
-            sq = fmaf(y, y, sq);
-          }
+        float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+        tmem_ld32_async(taddr0, v);
+        for (int ch = 0; ch < c2; ch += 64) {  // c2 % 64 == 0: two register buffers ping-pong
+          tmem_wait_ld();
+          tmem_ld32_async(taddr0 + ch + 32, v2);
+          stats32(v, s4, q4);
+          tmem_wait_ld();
+          if (ch + 64 < c2) tmem_ld32_async(taddr0 + ch + 64, v);
+          stats32(v2, s4, q4);
         }
+        const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]), sq = (q4[0] + q4[1]) + (q4[2] + q4[3]);
         const float mean = sum / (float)c2;
         const float var = fmaxf(sq / (float)c2 - mean * mean, 0.f);
         const float rstd = rsqrtf(var + ln_eps);
@@ -323,40 +367,78 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
       ph_acc++;
       tc_fence_after();
       {
-        float sum = 0.f, sq = 0.f;
-        for (int ch = 0; ch < c3; ch += 32) {
-          tmem_ld32(taddr0 + ch, v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float y = __uint_as_float(v[j]);
-            sum += y;
-            sq = fmaf(y, y, sq);
-          }
+        float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+        tmem_ld32_async(taddr0, v);
+        for (int ch = 0; ch < c3; ch += 64) {
+          tmem_wait_ld();
+          tmem_ld32_async(taddr0 + ch + 32, v2);
+          stats32(v, s4, q4);
+          tmem_wait_ld();
+          if (ch + 64 < c3) tmem_ld32_async(taddr0 + ch + 64, v);
+          stats32(v2, s4, q4);
         }
+        const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]), sq = (q4[0] + q4[1]) + (q4[2] + q4[3]);
         const float mean = sum / (float)c3;
         const float var = fmaxf(sq / (float)c3 - mean * mean, 0.f);
         const float rstd = rsqrtf(var + ln_eps);
         const float nmr = -mean * rstd;
-        const bool valid = n_in_cloud < N;
         named_bar(1 + s, 128);  // previous tile's combine has finished reading wkey
-        for (int ch = 0; ch < c3; ch += 32) {
-          tmem_ld32(taddr0 + ch, v);
-          uint32_t my_key = 0, my_lane = 0;
+        // Max over the warp's 32 points per channel without cross-lane reductions: every lane packs
+        // (value bits & ~31) | (31 - lane) -- post-ReLU floats are non-negative so the bit pattern is
+        // order-preserving, and the low 5 mantissa bits carry the lane so ties resolve to the smallest
+        // point index -- writes its 32 keys as one row of a warp-private 32x32 tile (XOR-swizzled float4
+        // chunks, conflict-free) in the slot's idle activation buffer, then reads back one COLUMN.
+        uint32_t* tr = reinterpret_cast<uint32_t*>(act) + q * 1024;  // 4 KB per warp
+        // Padding rows (n >= N) are staged as copies of the cloud's point 0, so they can only tie with a
+        // real point and the smallest-index rule drops them: no masking.  ReLU commutes with max, so it is
+        // applied once per (cloud, channel) in the finalize kernel; here keys are compared as SIGNED ints
+        // (any positive float beats any negative one; the order among negatives is irrelevant after ReLU).
+        const uint32_t lane_tag = 31u - (uint32_t)lane;
+        uint32_t st_off[8], ld_off[8];  // XOR-swizzled word offsets, hoisted out of the chunk loop
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float o = fmaf(fmaf(__uint_as_float(v[j]), rstd, nmr), g2[ch + j], be2[ch + j]);
-            o = valid ? fmaxf(o, 0.f) : 0.f;
-            const uint32_t bits = __float_as_uint(o);  // o >= 0: bit pattern is order-preserving
-            const uint32_t m = __reduce_max_sync(0xffffffffu, bits);
-            uint32_t win = 0;
-            if (want_argmax) win = __ffs(__ballot_sync(0xffffffffu, bits == m)) - 1;  // lowest lane = smallest index
-            if (lane == j) {
-              my_key = m;
-              my_lane = win;
+        for (int k = 0; k < 8; ++k) {
+          st_off[k] = (uint32_t)(lane * 32 + ((k ^ (lane & 7)) << 2));
+          ld_off[k] = (uint32_t)((((lane >> 2) ^ k) << 2) + (lane & 3));
+        }
+        auto reduce_chunk = [&](const uint32_t (&y)[32], int ch) {
+          uint32_t key[32];
+#pragma unroll
+          for (int j4 = 0; j4 < 32; j4 += 4) {
+            const float4 gg = *reinterpret_cast<const float4*>(g2 + ch + j4);
+            const float4 bb = *reinterpret_cast<const float4*>(be2 + ch + j4);
+            const float gv[4] = {gg.x, gg.y, gg.z, gg.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float o = fmaf(fmaf(__uint_as_float(y[j4 + e]), rstd, nmr), gv[e], bv[e]);
+              key[j4 + e] = (__float_as_uint(o) & ~31u) | lane_tag;
             }
           }
-          const uint32_t idx = (uint32_t)((int)(tile % tiles_per_cloud) * 128 + q * 32) + my_lane;
-          wkey[ch + lane] = ((unsigned long long)my_key << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+          __syncwarp();  // previous chunk's column reads are done
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4)
+            *reinterpret_cast<uint4*>(tr + st_off[c4]) =
+                make_uint4(key[4 * c4], key[4 * c4 + 1], key[4 * c4 + 2], key[4 * c4 + 3]);
+          __syncwarp();
+          int m0 = INT_MIN, m1 = INT_MIN;  // two independent max chains
+#pragma unroll
+          for (int p = 0; p < 32; p += 4) {
+            m0 = __vimax3_s32(m0, (int)tr[p * 32 + ld_off[p & 7]], (int)tr[(p + 1) * 32 + ld_off[(p + 1) & 7]]);
+            m1 = __vimax3_s32(m1, (int)tr[(p + 2) * 32 + ld_off[(p + 2) & 7]], (int)tr[(p + 3) * 32 + ld_off[(p + 3) & 7]]);
+          }
+          const uint32_t m = (uint32_t)max(m0, m1);
+          // lane now owns channel ch + lane: m = max key over this warp's 32 points.  Flipping the sign bit
+          // turns the signed order into an unsigned one for the packed u64 atomicMax across warps / tiles.
+          const uint32_t idx = (uint32_t)((int)(tile % tiles_per_cloud) * 128 + q * 32) + (31u - (m & 31u));
+          wkey[ch + lane] = ((unsigned long long)((m & ~31u) ^ 0x80000000u) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+        };
+        tmem_ld32_async(taddr0, v);
+        for (int ch = 0; ch < c3; ch += 64) {
+          tmem_wait_ld();
+          tmem_ld32_async(taddr0 + ch + 32, v2);
+          reduce_chunk(v, ch);
+          tmem_wait_ld();
+          if (ch + 64 < c3) tmem_ld32_async(taddr0 + ch + 64, v);
+          reduce_chunk(v2, ch + 32);
         }
         tc_fence_before();
         mbar_arrive(BAR(11 + s));  // accumulator drained: the MMA warp may start this slot's next tile
@@ -385,7 +467,7 @@ __global__ void pool_finalize_kernel(const unsigned long long* __restrict__ keys
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned long long k = keys[i];
-  pooled[i] = __uint_as_float((uint32_t)(k >> 32));
+  pooled[i] = fmaxf(__uint_as_float((uint32_t)(k >> 32) ^ 0x80000000u), 0.f);  // undo the sign flip; ReLU after max
   if (argmax) argmax[i] = (int32_t)(0xFFFFFFFFu - (uint32_t)k);
 }
 
@@ -431,8 +513,9 @@ __global__ void pack_weights_kernel(const float* __restrict__ w0, const float* _
 }
 
 static bool shapes_ok(int c1, int c2, int c3) {
-  auto ok = [](int c) { return c >= 32 && c <= 256 && c % 32 == 0; };
-  return ok(c1) && ok(c2) && ok(c3) && make_layout(c1, c2, c3).total <= 227 * 1024;
+  auto ok = [](int c, int m) { return c >= m && c <= 256 && c % m == 0; };
+  // activation buffer doubles as the 16 KB max-pool transpose scratch: needs max(c1, c2) >= 64
+  return ok(c1, 32) && ok(c2, 64) && ok(c3, 64) && (c1 >= 64 || c2 >= 64) && make_layout(c1, c2, c3).total <= 227 * 1024;
 }
 
 }  // namespace tc

@@ -22,7 +22,10 @@ __global__ void __launch_bounds__(256) stage_points_kernel(
     uint32_t stream_id, float* __restrict__ xf, __nv_bfloat16* __restrict__ xh) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (int64_t)B * NP) return;
-  const int b = (int)(t / NP), n = (int)(t % NP);
+  const int b = (int)(t / NP), n_out = (int)(t % NP);
+  // padding rows (n_out >= N) replicate the cloud's point 0, augmentation draw included: a duplicate can only
+  // tie with the real point and the smallest-index rule of the max-pool then drops it (no masking downstream)
+  const int n = n_out < N ? n_out : 0;
   const int C = 3 + (rgb ? 3 : 0) + n_pos + n_seg;
   const uint64_t cnt = counter_dev ? *counter_dev : 0ull;
 
@@ -30,8 +33,8 @@ __global__ void __launch_bounds__(256) stage_points_kernel(
 #pragma unroll
   for (int c = 0; c < CP; ++c) f[c] = 0.f;
   float rgb_raw[3] = {0.f, 0.f, 0.f};
-  const bool real = n < N;
-  if (real) {
+  const bool real = true;
+  {
     const float* px = xyz + (int64_t)b * 3 * N + n;
     f[0] = px[0];
     f[1] = px[N];
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(256) stage_points_kernel(
     f[0] = x;
     f[1] = y;
     f[2] = z;
-    float4* dst = reinterpret_cast<float4*>(xf + ((int64_t)r * NP + n) * CP);
+    float4* dst = reinterpret_cast<float4*>(xf + ((int64_t)r * NP + n_out) * CP);
 #pragma unroll
     for (int q = 0; q < CP / 4; ++q) dst[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
 
@@ -121,9 +124,9 @@ __global__ void __launch_bounds__(256) stage_points_kernel(
 #pragma unroll
         for (int k = 0; k < 3; ++k) h[C + 1 + k] = __float2bfloat16(f[k] - __bfloat162float(h[k]));
       }
-      const int64_t tile = ((int64_t)r * NP + n) >> 7;
+      const int64_t tile = ((int64_t)r * NP + n_out) >> 7;
       char* base = reinterpret_cast<char*>(xh) + tile * 4096;
-      const int p = n & 127;
+      const int p = n_out & 127;
       *reinterpret_cast<uint4*>(base + xh_tile_offset(p, 0)) = *reinterpret_cast<uint4*>(&h[0]);
       *reinterpret_cast<uint4*>(base + xh_tile_offset(p, 8)) = *reinterpret_cast<uint4*>(&h[8]);
     }

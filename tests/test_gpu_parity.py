@@ -140,7 +140,7 @@ def test_stage_points(L, aug):
         assert torch.allclose(got, x_ref, atol=1e-6)
     else:
         assert torch.equal(got, x_ref)
-    assert float(xf[:, N:].abs().max()) == 0.0
+    assert torch.equal(xf[:, N:], xf[:, :1].expand(-1, NP - N, -1))  # padding rows replicate point 0
     if C < CP:
         assert float(xf[:, :, C:].abs().max()) == 0.0
 
