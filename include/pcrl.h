@@ -115,12 +115,14 @@ int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, cons
  * stride ldy.  relu: 0/1.
  * pcrl_linear_bwd: given dy [M,Nout] (already masked by the caller's activation) computes
  *   dw += dy^T x, db += colsum(dy) (skipped when dw / db are NULL), and (if dx != NULL) dx = dy W
- *   (dx row stride lddx).
+ *   (dx row stride lddx).  relu_mask (optional, [M,K] row stride ld_mask): the post-ReLU input x itself --
+ *   dx is zeroed where relu_mask <= 0, i.e. the previous layer's ReLU backward fused into this GEMM's epilogue.
  * ------------------------------------------------------------------------------------------- */
 int pcrl_linear_fwd(const float* x, int ldx, const float* w, const float* b, float* y, int ldy, int M, int K,
                     int Nout, int relu, int tf32, void* stream);
 int pcrl_linear_bwd(const float* x, int ldx, const float* w, const float* dy, int lddy, float* dw, float* db,
-                    float* dx, int lddx, int M, int K, int Nout, int tf32, void* stream);
+                    float* dx, int lddx, const float* relu_mask, int ld_mask, int M, int K, int Nout, int tf32,
+                    void* stream);
 /* tf32 != 0: run the GEMMs on the tcgen05 TF32 tensor-core kernel (TMA-fed, fp32 inputs consumed as TF32)
  * whenever the operands meet TMA's alignment rules (16-byte base, row pitch % 4 == 0), else and for
  * tf32 == 0 the exact-fp32 FFMA kernel runs.

@@ -93,6 +93,9 @@ struct GemmArgs {
   int split_k;
   const int* m_dev;   // if set, rows i >= *m_dev are skipped (M rows)
   const int* k_dev;   // if set, contraction index l >= *k_dev is skipped (K)
+  const float* mask;  // if set: C[i][j] = 0 where mask[i*ldmask + j] <= 0 (ReLU backward fused into the dgrad GEMM)
+  int64_t ldmask;
+  int bn_hint;        // tensor-core path only: force the output tile width (0 = auto)
 };
 int launch_sgemm(const GemmArgs& g, cudaStream_t st);
 

@@ -46,7 +46,7 @@ int launch_gemm(const GemmArgs& g, int tf32, cudaStream_t st) {
     t.bias = g.bias; t.C = g.C; t.ldc = g.ldc; t.M = g.M; t.N = g.N; t.K = g.K; t.relu = g.relu;
     t.split_k = g.split_k;
     t.mode = g.accumulate ? (g.split_k > 1 ? 2 : 1) : 0;
-    t.k_dev = g.k_dev; t.m_dev = g.m_dev;
+    t.k_dev = g.k_dev; t.m_dev = g.m_dev; t.mask = g.mask; t.ldmask = g.ldmask; t.bn_hint = g.bn_hint;
     if (g.K >= 8 && tcg::tc_gemm_supported(t)) return tcg::launch_tc_gemm(t, st);
   }
   return launch_sgemm(g, st);
@@ -64,6 +64,49 @@ int launch_zero_tail(float* x, int width, const int* count_dev, int capacity_row
   zero_tail_kernel<<<8, 256, 0, st>>>(x, width, count_dev, capacity_rows);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
+}
+
+// ---- single-output layers (the Q heads' last Linear, Nout == 1): matrix-vector kernels instead of a GEMM tile
+// y[m] = x[m,:] . w + b   -- one warp per row
+__global__ void __launch_bounds__(256) gemv_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
+                                                       const float* __restrict__ b, float* __restrict__ y, int64_t ldy,
+                                                       int M, int K, int relu) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + (int64_t)row * ldx;
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) s = fmaf(xr[k], __ldg(w + k), s);
+  s = warp_sum(s);
+  if (lane == 0) {
+    s += b ? b[0] : 0.f;
+    y[(int64_t)row * ldy] = relu ? fmaxf(s, 0.f) : s;
+  }
+}
+// dw[k] += sum_m dy[m] x[m,k];  db += sum_m dy[m];  dx[m,k] = dy[m] w[k] (masked by relu_mask > 0 if given)
+__global__ void __launch_bounds__(256) gemv_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
+                                                       const float* __restrict__ dy, int64_t lddy, float* __restrict__ dw,
+                                                       float* __restrict__ db, float* __restrict__ dx, int64_t lddx,
+                                                       const float* __restrict__ mask, int64_t ldmask, int M, int K) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int m0 = blockIdx.y * rows_per, m1 = min(M, m0 + rows_per);
+  const float wk = (k < K) ? w[k] : 0.f;
+  float acc = 0.f, accb = 0.f;
+#pragma unroll 4
+  for (int m = m0; m < m1; ++m) {
+    const float g = __ldg(dy + (int64_t)m * lddy);
+    if (k < K) {
+      if (dw) acc = fmaf(g, __ldg(x + (int64_t)m * ldx + k), acc);
+      if (dx) {
+        float v = g * wk;
+        if (mask && !(__ldg(mask + (int64_t)m * ldmask + k) > 0.f)) v = 0.f;
+        dx[(int64_t)m * lddx + k] = v;
+      }
+    }
+    accb += g;
+  }
+  if (k < K && dw) atomicAdd(dw + k, acc);
+  if (db && k == 0) atomicAdd(db, accb);
 }
 
 __global__ void relu_bwd_kernel(float* __restrict__ dy, const float* __restrict__ y, int64_t n) {
@@ -99,6 +142,11 @@ extern "C" {
 int pcrl_linear_fwd(const float* x, int ldx, const float* w, const float* b, float* y, int ldy, int M, int K,
                     int Nout, int relu, int tf32, void* stream) {
   PCRL_CHECK_ARG(x && w && y && M >= 0 && K > 0 && Nout > 0 && ldx >= K && ldy >= Nout);
+  if (Nout == 1 && M > 0) {
+    gemv_fwd_kernel<<<(unsigned)cdiv((int64_t)M * 32, 256), 256, 0, as_stream(stream)>>>(x, ldx, w, b, y, ldy, M, K, relu);
+    PCRL_CHECK_LAUNCH();
+    return PCRL_OK;
+  }
   GemmArgs g{};
   g.A = x; g.a_si = ldx; g.a_sl = 1;
   g.B = w; g.b_sl = 1; g.b_sj = K;
@@ -109,9 +157,16 @@ int pcrl_linear_fwd(const float* x, int ldx, const float* w, const float* b, flo
 }
 
 int pcrl_linear_bwd(const float* x, int ldx, const float* w, const float* dy, int lddy, float* dw, float* db,
-                    float* dx, int lddx, int M, int K, int Nout, int tf32, void* stream) {
+                    float* dx, int lddx, const float* relu_mask, int ld_mask, int M, int K, int Nout, int tf32,
+                    void* stream) {
   PCRL_CHECK_ARG(x && w && dy && M >= 0 && K > 0 && Nout > 0);
   cudaStream_t st = as_stream(stream);
+  if (Nout == 1 && M > 0) {
+    dim3 grid((unsigned)cdiv(K, 256), (unsigned)std::min<int64_t>(cdiv(M, 8), 128));
+    gemv_bwd_kernel<<<grid, 256, 0, st>>>(x, ldx, w, dy, lddy, dw, db, dx, lddx, relu_mask, ld_mask, M, K);
+    PCRL_CHECK_LAUNCH();
+    return PCRL_OK;
+  }
   // dw[n][k] += sum_m dy[m][n] * x[m][k]
   GemmArgs g{};
   g.A = dy; g.a_si = 1; g.a_sl = lddy;
@@ -122,7 +177,8 @@ int pcrl_linear_bwd(const float* x, int ldx, const float* w, const float* dy, in
   // enough CTAs to fill the machine: tiles * split_k >= ~2 waves
   const int tile = tf32 ? 128 : 64;
   int64_t tiles = cdiv(Nout, tile) * cdiv(K, tile);
-  int split = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv((tf32 ? 1 : 2) * sm_count(), tiles), cdiv(M, tile)));
+  int split = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(2 * sm_count(), tiles), cdiv(M, tile)));
+  if (tf32) split = (M >= 8192) ? (int)std::min<int64_t>(32, cdiv(M, 2048)) : 1;  // few atomics per address; narrow tiles fill the SMs
   g.split_k = split;
   int rc = 0;
   if (dw && (rc = launch_gemm(g, tf32, st))) return rc;
@@ -138,6 +194,7 @@ int pcrl_linear_bwd(const float* x, int ldx, const float* w, const float* dy, in
     h.C = dx; h.ldc = lddx;
     h.M = M; h.N = K; h.K = Nout;
     h.split_k = 1;
+    h.mask = relu_mask; h.ldmask = ld_mask;  // dx *= (x_post_activation > 0), fused
     rc = launch_gemm(h, tf32, st);
     if (rc) return rc;
   }

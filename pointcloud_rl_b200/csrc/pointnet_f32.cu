@@ -165,14 +165,15 @@ static int gemm_nt(const float* A, int lda, const float* W, int ldw, const float
   return launch_gemm(g, tf32, st);
 }
 static int gemm_nn(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int K, int Nout,
-                   const int* m_dev, cudaStream_t st, int tf32 = 0) {
-  // C[M,Nout] = A[M,K] W[K,Nout]
+                   const int* m_dev, cudaStream_t st, int tf32 = 0, const float* relu_mask = nullptr) {
+  // C[M,Nout] = (A[M,K] W[K,Nout]) * (relu_mask > 0)
   GemmArgs g{};
   g.A = A; g.a_si = lda; g.a_sl = 1;
   g.B = W; g.b_sl = ldw; g.b_sj = 1;
   g.C = C; g.ldc = ldc;
   g.M = M; g.N = Nout; g.K = K;
   g.split_k = 1; g.m_dev = m_dev;
+  g.mask = relu_mask; g.ldmask = ldc;
   return launch_gemm(g, tf32, st);
 }
 static int gemm_tn_acc(const float* A, int lda, const float* Bm, int ldb, float* C, int ldc, int Mrows, int Na, int Nb,
@@ -186,7 +187,13 @@ static int gemm_tn_acc(const float* A, int lda, const float* Bm, int ldb, float*
   g.accumulate = 1; g.k_dev = rows_dev;
   const int tile = tf32 ? 128 : 64;
   int64_t tiles = cdiv(Na, tile) * cdiv(Nb, tile);
-  g.split_k = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv((tf32 ? 2 : 4) * sm_count(), tiles), cdiv(expected_rows, 128)));
+  g.split_k = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(4 * sm_count(), tiles), cdiv(expected_rows, 128)));
+  if (tf32) {
+    // full-width tiles (every operand panel streamed once per M tile) and just enough K-splits to fill the SMs
+    g.bn_hint = Nb >= 128 ? 128 : (Nb > 32 ? 64 : 32);
+    const int64_t t128 = cdiv(Na, 128) * cdiv(Nb, g.bn_hint);
+    g.split_k = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(sm_count(), t128), cdiv(expected_rows, 256)));
+  }
   return launch_gemm(g, tf32, st);
 }
 
@@ -325,16 +332,12 @@ int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, cons
     if ((rc = launch_zero_tail(w.xa, CP, w.total, A, st))) return rc;
   }
   if ((rc = gemm_tn_acc(w.d2, c3, w.h1, c2, dw2, c2, A, c3, c2, w.total, expect, st, tf32))) return rc;
-  if ((rc = gemm_nn(w.d2, c3, w2, c2, w.d1, c2, A, c3, c2, w.total, st, tf32))) return rc;
-  relu_bwd_rows_kernel<<<sm_count() * 4, 256, 0, st>>>(w.d1, w.h1, c2, w.total);
-  PCRL_CHECK_LAUNCH();
+  if ((rc = gemm_nn(w.d2, c3, w2, c2, w.d1, c2, A, c3, c2, w.total, st, tf32, w.h1))) return rc;  // ReLU bwd fused
   // 5. layer 1 backward
   if ((rc = launch_ln_rows_bwd(w.d1, c2, w.y1hat, w.rstd1, g1, dg1, dbe1, w.d1, c2, A, c2, w.total, st))) return rc;
   if (tf32 && (rc = launch_zero_tail(w.d1, c2, w.total, A, st))) return rc;
   if ((rc = gemm_tn_acc(w.d1, c2, w.h0, c1, dw1, c1, A, c2, c1, w.total, expect, st, tf32))) return rc;
-  if ((rc = gemm_nn(w.d1, c2, w1, c1, w.d0, c1, A, c2, c1, w.total, st, tf32))) return rc;
-  relu_bwd_rows_kernel<<<sm_count() * 4, 256, 0, st>>>(w.d0, w.h0, c1, w.total);
-  PCRL_CHECK_LAUNCH();
+  if ((rc = gemm_nn(w.d1, c2, w1, c1, w.d0, c1, A, c2, c1, w.total, st, tf32, w.h0))) return rc;  // ReLU bwd fused
   // 6. layer 0 backward: dW0 [c1,C] += d0^T xa[:, :C];  db0 += colsum(d0)
   if (tf32 && (rc = launch_zero_tail(w.d0, c1, w.total, A, st))) return rc;
   // layer-0 weight gradient stays on exact-fp32 FFMA: raw coordinates lose too much under TF32 truncation, and N = C is tiny

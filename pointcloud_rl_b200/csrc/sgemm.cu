@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
         atomicAdd(c, v);
       } else {
         if (g.relu) v = fmaxf(v, 0.f);
+        if (g.mask && !(g.mask[(int64_t)gi * g.ldmask + gj] > 0.f)) v = 0.f;
         *c = v;
       }
     }
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
 int launch_sgemm(const GemmArgs& g, cudaStream_t st) {
   PCRL_CHECK_ARG(g.M >= 0 && g.N >= 0 && g.K >= 0 && g.split_k >= 1);
   PCRL_CHECK_ARG(g.split_k == 1 || (g.accumulate && !g.relu));
+  PCRL_CHECK_ARG(!g.mask || !g.accumulate);
   if (g.M == 0 || g.N == 0) return PCRL_OK;
   dim3 grid((unsigned)cdiv(g.N, BN), (unsigned)cdiv(g.M, BM), (unsigned)g.split_k);
   sgemm_kernel<<<grid, 256, 0, st>>>(g);

@@ -27,6 +27,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -107,8 +110,13 @@ struct Params {
   int stages;
   const int* k_dev;  // optional device-side bound on the contraction length
   const int* m_dev;  // optional device-side bound on M
+  const float* mask;  // optional [M, N] post-activation tensor: C = (mask > 0) ? value : 0  (fused ReLU backward)
+  int64_t ldmask;
 };
 
+// Persistent: each CTA walks output tiles t = blockIdx.x, += gridDim.x.  The smem ring and its phases run
+// continuously across tiles, and the accumulator is double-buffered in TMEM (2 x bn columns) so the epilogue
+// of tile n overlaps the loads and MMAs of tile n+1.
 template <int TMEM_COLS>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Params P) {
@@ -119,27 +127,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_bytes = BM * BK * 4, b_bytes = (uint32_t)P.bn * BK * 4;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  const uint32_t bar0 = sbase + (uint32_t)P.stages * stage_bytes;  // full[s], empty[s], acc
+  const uint32_t bar0 = sbase + (uint32_t)P.stages * stage_bytes;  // full[s], empty[s], acc_full[2], acc_empty[2]
   auto FULL = [&](int s) { return bar0 + 8u * s; };
   auto EMPTY = [&](int s) { return bar0 + 8u * (P.stages + s); };
-  const uint32_t ACC = bar0 + 8u * (2 * P.stages);
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + (size_t)P.stages * stage_bytes + 8 * (2 * P.stages + 1));
+  auto ACC_FULL = [&](int b) { return bar0 + 8u * (2 * P.stages + b); };
+  auto ACC_EMPTY = [&](int b) { return bar0 + 8u * (2 * P.stages + 2 + b); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + (size_t)P.stages * stage_bytes + 8 * (2 * P.stages + 4));
 
   const int K = P.k_dev ? min(P.K, *P.k_dev) : P.K;
+  const int Mlim = P.m_dev ? min(P.M, *P.m_dev) : P.M;
   const int kb_total = (K + BK - 1) / BK;
   const int kb_per = (kb_total + P.split_k - 1) / P.split_k;
-  const int kb0 = blockIdx.z * kb_per;
-  const int kb1 = min(kb_total, kb0 + kb_per);
-  const int nkb = max(kb1 - kb0, 0);
-  const int i0 = blockIdx.y * BM, j0 = blockIdx.x * P.bn;
-  if (P.m_dev && i0 >= *P.m_dev) return;  // whole tile past the device-side row count (before any allocation)
+  const int nt = (P.N + P.bn - 1) / P.bn, mt = (P.M + BM - 1) / BM;
+  const int total_tiles = nt * mt * P.split_k;
+  // tile -> (k-split z, M tile, N tile); N fastest so concurrently running CTAs share the same A rows in L2
+  auto tile_coords = [&](int t, int& z, int& i0, int& j0, int& kb0, int& nkb) {
+    z = t / (nt * mt);
+    const int rem = t - z * nt * mt;
+    i0 = (rem / nt) * BM;
+    j0 = (rem % nt) * P.bn;
+    kb0 = z * kb_per;
+    nkb = max(min(kb_total, kb0 + kb_per) - kb0, 0);
+    return i0 < Mlim && nkb > 0;  // tiles past the device-side row count / empty K slices are skipped by every role
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) {
       mbar_init(FULL(s), 1);
       mbar_init(EMPTY(s), 1);
     }
-    mbar_init(ACC, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(ACC_FULL(b), 1);
+      mbar_init(ACC_EMPTY(b), 128);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -153,12 +173,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (nkb > 0) {
-    if (warp == 0) {
-      if (lane == 0) {
-        for (int kb = 0; kb < nkb; ++kb) {
-          const int s = kb % P.stages;
-          if (kb >= P.stages) mbar_wait(EMPTY(s), ((kb / P.stages) - 1) & 1);
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;  // running k-block count: ring slot = it % stages, phase = (it / stages) & 1
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int z, i0, j0, kb0, nkb;
+        if (!tile_coords(t, z, i0, j0, kb0, nkb)) continue;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % P.stages;
+          mbar_wait(EMPTY(s), ((it / P.stages) & 1) ^ 1);  // passes immediately on the first lap
           mbar_expect_tx(FULL(s), stage_bytes);
           const uint32_t sa = sbase + s * stage_bytes, sb = sa + a_bytes;
           const int l0 = (kb0 + kb) * BK;
@@ -174,12 +198,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       }
-    } else if (warp == 1) {
-      if (lane == 0) {
-        const uint32_t idesc = idesc_tf32(P.bn, P.a_mn, P.b_mn);
-        for (int kb = 0; kb < nkb; ++kb) {
-          const int s = kb % P.stages;
-          mbar_wait(FULL(s), (kb / P.stages) & 1);
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(P.bn, P.a_mn, P.b_mn);
+      uint32_t it = 0, n = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int z, i0, j0, kb0, nkb;
+        if (!tile_coords(t, z, i0, j0, kb0, nkb)) continue;
+        const uint32_t buf = n & 1;
+        mbar_wait(ACC_EMPTY(buf), ((n >> 1) & 1) ^ 1);  // epilogue drained this accumulator (free on first use)
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * (uint32_t)P.bn;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % P.stages;
+          mbar_wait(FULL(s), (it / P.stages) & 1);
           tc_fence_after();
           const uint32_t sa = sbase + s * stage_bytes, sb = sa + a_bytes;
 #pragma unroll
@@ -187,29 +221,37 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // K-major: +32 B inside the 128 B swizzle row per 8-element K step; MN-major: next 8-row group
             const uint64_t ad = P.a_mn ? desc_mnmajor(sa + ks * 1024) : desc_kmajor(sa + ks * 32);
             const uint64_t bd = P.b_mn ? desc_mnmajor(sb + ks * 1024) : desc_kmajor(sb + ks * 32);
-            mma_tf32(tmem_base, ad, bd, idesc, (kb | ks) != 0);
+            mma_tf32(d_tmem, ad, bd, idesc, (kb | ks) != 0);
           }
           mma_commit(EMPTY(s));
         }
-        mma_commit(ACC);
+        mma_commit(ACC_FULL(buf));
+        ++n;
       }
-    } else {
-      // epilogue: warp (2..5) -> TMEM lane quadrant warp%4
-      const int q = warp & 3;
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: warp (2..5) -> TMEM lane quadrant warp%4
+    const int q = warp & 3;
+    uint32_t n = 0;
+    uint32_t v[32];
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int z, i0, j0, kb0, nkb;
+      if (!tile_coords(t, z, i0, j0, kb0, nkb)) continue;
+      const uint32_t buf = n & 1;
       const int row = i0 + q * 32 + lane;
-      mbar_wait(ACC, 0);
+      mbar_wait(ACC_FULL(buf), (n >> 1) & 1);
       tc_fence_after();
-      uint32_t v[32];
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)P.bn;
       for (int c = 0; c < P.bn; c += 32) {
         if (c + 32 <= P.bn) {
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, v);
+          tmem_ld32(tbase + c, v);
         } else {
           // bn == 16 / 48 / ...: a 16-column tail
           asm volatile(
               "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-              : "r"(tmem_base + ((uint32_t)(q * 32) << 16) + c));
+              : "r"(tbase + c));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         }
         const int ncol = min(32, P.bn - c);
@@ -220,12 +262,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int j4 = 0; j4 < 32; j4 += 4) {
             if (j4 >= ncol) break;
             float o[4];
+            float mk[4] = {1.f, 1.f, 1.f, 1.f};
+            if (P.mask) {
+              const float* mrow = P.mask + (int64_t)row * P.ldmask + j0 + c + j4;
+              if (((reinterpret_cast<uintptr_t>(mrow) & 15) == 0) && (j0 + c + j4 + 4 <= P.N)) {
+                const float4 m4 = __ldg(reinterpret_cast<const float4*>(mrow));
+                mk[0] = m4.x; mk[1] = m4.y; mk[2] = m4.z; mk[3] = m4.w;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (j0 + c + j4 + e < P.N) mk[e] = __ldg(mrow + e);
+              }
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int col = j0 + c + j4 + e;
               float x = __uint_as_float(v[j4 + e]);
-              if (P.bias && blockIdx.z == 0 && col < P.N) x += __ldg(P.bias + col);
+              if (P.bias && z == 0 && col < P.N) x += __ldg(P.bias + col);
               if (P.relu) x = fmaxf(x, 0.f);
+              if (!(mk[e] > 0.f)) x = 0.f;
               o[e] = x;
             }
             if (P.mode == 0 && vec_ok) {
@@ -243,15 +298,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       }
+      tc_fence_before();
+      mbar_arrive(ACC_EMPTY(buf));  // all 128 epilogue threads: this accumulator may be overwritten
+      ++n;
     }
-  } else if (P.mode == 0 && blockIdx.z == 0 && warp >= 2) {
-    // empty contraction: C = act(bias)
-    const int row = i0 + (warp & 3) * 32 + lane;
-    if (row < P.M)
-      for (int c = 0; c < P.bn && j0 + c < P.N; ++c) {
-        float x = P.bias ? P.bias[j0 + c] : 0.f;
-        P.C[(int64_t)row * P.ldc + j0 + c] = P.relu ? fmaxf(x, 0.f) : x;
-      }
   }
 
   tc_fence_before();
@@ -317,13 +367,22 @@ int launch_tc_gemm(const TcGemmArgs& g, cudaStream_t st) {
   else if (g.N <= 32) bn = 32;
   else if (g.N <= 64 && bn > 64) bn = 64;
   if (g.b_mn && bn < 32) bn = 32;  // MN-major B is loaded in 32-column boxes
+  if (g.bn_hint) bn = g.bn_hint;
   Params P{};
   P.C = g.C; P.ldc = g.ldc; P.bias = g.bias; P.M = g.M; P.N = g.N; P.K = g.K; P.bn = bn; P.a_mn = g.a_mn; P.b_mn = g.b_mn;
   P.relu = g.relu; P.mode = g.mode; P.split_k = g.split_k; P.k_dev = g.k_dev; P.m_dev = g.m_dev;
+  P.mask = g.mask; P.ldmask = g.ldmask;
   PCRL_CHECK_ARG(g.split_k >= 1 && (g.split_k == 1 || (g.mode == 2 && !g.relu)));
   const uint32_t stage_bytes = BM * BK * 4 + bn * BK * 4;
-  P.stages = (int)std::min<int64_t>(6, std::max<int64_t>(2, (200 * 1024) / stage_bytes));
-  const size_t smem = (size_t)P.stages * stage_bytes + 8 * (2 * P.stages + 2) + 16 + 1024;
+  const int64_t n_tiles = mt * cdiv(g.N, bn) * g.split_k;
+  const int64_t kb_max = cdiv(cdiv(g.K, BK), g.split_k);
+  if (kb_max < 1) return PCRL_OK;
+  // ring depth: enough to cover the K loop of a tile (plus prefetch into the next tile), capped by smem; short-K
+  // tall-skinny problems keep the ring small so two CTAs fit on an SM
+  const int64_t budget = (n_tiles >= 2 * sms && kb_max <= 8) ? 100 * 1024 : 200 * 1024;
+  P.stages = (int)std::min<int64_t>(std::min<int64_t>(8, std::max<int64_t>(3, 2 * kb_max)), std::max<int64_t>(2, budget / stage_bytes));
+  const size_t smem = (size_t)P.stages * stage_bytes + 8 * (2 * P.stages + 5) + 16 + 1024;
+  const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / smem));
 
   CUtensorMap ma, mb;
   bool okm;
@@ -337,11 +396,11 @@ int launch_tc_gemm(const TcGemmArgs& g, cudaStream_t st) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    PCRL_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PCRL_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  dim3 grid((unsigned)cdiv(g.N, bn), (unsigned)mt, (unsigned)g.split_k);
-  tc_gemm_kernel<128><<<grid, kThreads, smem, st>>>(ma, mb, P);
+  const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)sms * ctas_per_sm);
+  tc_gemm_kernel<256><<<grid, kThreads, smem, st>>>(ma, mb, P);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }

@@ -21,6 +21,9 @@ struct TcGemmArgs {
   int split_k;
   const int* k_dev;  // optional device bound on the contraction length (rows beyond it must be zero up to a multiple of 32)
   const int* m_dev;  // optional device bound on M: tiles past it exit immediately
+  const float* mask; // optional [M,N] post-activation tensor: output zeroed where mask <= 0 (fused ReLU backward)
+  int64_t ldmask;
+  int bn_hint;       // 0 = choose the output tile width automatically
 };
 
 bool tc_gemm_supported(const TcGemmArgs& g);

@@ -350,12 +350,13 @@ class UpdateEngine:
         p, g, w, (h1n, h2n) = self.p, self.g, self.w, self.spec.hidden
         h1, h2 = w[f"h1_{keep}"], w[f"h2_{keep}"]
         gw = (lambda n: g[f"{net}.{n}"]) if want_w else (lambda n: None)
-        self.L.linear_bwd(h2, h2n, p[f"{net}.w2"], dout, lddo, gw("w2"), gw("b2"), w["dh2"], h2n, M, h2n, nout, self.tf32, st)
-        self.L.relu_bwd(w["dh2"], h2, M * h2n, st)
-        self.L.linear_bwd(h1, h1n, p[f"{net}.w1"], w["dh2"], h2n, gw("w1"), gw("b1"), w["dh1"], h1n, M, h1n, h2n, self.tf32, st)
-        self.L.relu_bwd(w["dh1"], h1, M * h1n, st)
+        # each layer's dX GEMM applies the previous ReLU's backward in its epilogue (mask = saved post-activation)
+        self.L.linear_bwd(h2, h2n, p[f"{net}.w2"], dout, lddo, gw("w2"), gw("b2"), w["dh2"], h2n, h2, h2n, M, h2n, nout,
+                          self.tf32, st)
+        self.L.linear_bwd(h1, h1n, p[f"{net}.w1"], w["dh2"], h2n, gw("w1"), gw("b1"), w["dh1"], h1n, h1, h1n, M, h1n, h2n,
+                          self.tf32, st)
         self.L.linear_bwd(x, x.stride(0), p[f"{net}.w0"], w["dh1"], h1n, gw("w0"), gw("b0"), dx,
-                          dx.stride(0) if dx is not None else 0, M, K, h1n, self.tf32, st)
+                          dx.stride(0) if dx is not None else 0, None, 0, M, K, h1n, self.tf32, st)
 
     def _adam(self, group, idx, lr, betas, gradsq_slot, polyak, st):
         lo, hi = self.layout.group_range[group]
@@ -423,7 +424,7 @@ class UpdateEngine:
         L.layernorm_bwd(w["dz"], D, w["xhat_obs"], w["rstd_obs"], p["pn.gf"], self.g["pn.gf"], self.g["pn.bef"],
                         w["dz"], R, D, st)
         L.linear_bwd(w["pooled_obs"], c3, p["pn.wf"], w["dz"], D, self.g["pn.wf"], self.g["pn.bf"], w["dpooled"], c3,
-                     R, c3, D, self.tf32, st)
+                     None, 0, R, c3, D, self.tf32, st)
         g = self.g
         L.pointnet_bwd(w["xf_obs"], R, sp.n_points, sp.NP, sp.CP, sp.C, w["pooled_obs"], w["argmax_obs"], w["dpooled"],
                        p["pn.w0"], p["pn.b0"], p["pn.w1"], p["pn.g1"], p["pn.be1"], p["pn.w2"], p["pn.g2"],

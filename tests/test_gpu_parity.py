@@ -58,7 +58,7 @@ def test_linear_fwd_bwd(L, M, K, N, relu):
     dw = torch.zeros(N, K, device="cuda")
     db = torch.zeros(N, device="cuda")
     dx = torch.empty(M, K, device="cuda")
-    L.linear_bwd(xd, K, wd, dyd, N, dw, db, dx, K, M, K, N, 0, sp())
+    L.linear_bwd(xd, K, wd, dyd, N, dw, db, dx, K, None, 0, M, K, N, 0, sp())
     assert rel_err(dw, wr.grad) < 1e-5
     assert rel_err(db, br.grad) < 1e-5
     assert rel_err(dx, xr.grad) < 1e-5
@@ -330,10 +330,14 @@ def test_linear_tf32_path(L, M, K, N):
     L.linear_fwd(x.cuda(), K, w.cuda(), b.cuda(), y, N, M, K, N, 1, 1, sp())
     assert float((y.cpu().double() - torch.relu(pre)).abs().max()) < 2e-2 and float(y.min()) >= 0.0
     dw, db, dx = torch.zeros(N, K, device="cuda"), torch.zeros(N, device="cuda"), torch.empty(M, K, device="cuda")
-    L.linear_bwd(x.cuda(), K, w.cuda(), dy.cuda(), N, dw, db, dx, K, M, K, N, 1, sp())
+    L.linear_bwd(x.cuda(), K, w.cuda(), dy.cuda(), N, dw, db, dx, K, None, 0, M, K, N, 1, sp())
     assert rel_err(dw, dy.double().t() @ x.double()) < 2e-3
     assert rel_err(dx, dy.double() @ w.double()) < 2e-3
     assert rel_err(db, dy.double().sum(0)) < 1e-5
+    # fused ReLU backward: dx zeroed where the saved post-activation input is <= 0
+    xm = torch.relu(x)
+    L.linear_bwd(xm.cuda(), K, w.cuda(), dy.cuda(), N, None, None, dx, K, xm.cuda(), K, M, K, N, 1, sp())
+    assert rel_err(dx, (dy.double() @ w.double()) * (xm > 0)) < 2e-3
 
 
 # ------------------------------------------------------------------------------------------ full update
