@@ -7,13 +7,13 @@
 //
 // Points sit on the MMA M axis (128 TMEM lanes = 128 points), channels along TMEM columns, so after a
 // 32x32b tcgen05.ld every thread owns one point's channel row: LayerNorm statistics are thread-local
-// and the max over points is the cross-lane direction (redux.sync + ballot).
+// and the max over points is the cross-lane direction (a warp-private shared-memory transpose).
 //
-// Persistent kernel, one CTA per SM, 10 warps:
-//   warp 0      TMA producer: weights once (cp.async.bulk), then the 4 KB point tiles through a 4-stage ring
-//   warp 1      MMA issuer (one elected thread), ping-pongs two tile slots
-//   warps 2-5   epilogue of slot 0   } each slot owns 256 TMEM columns and one activation buffer; while one
-//   warps 6-9   epilogue of slot 1   } slot's epilogue normalises layer k, the tensor core runs the other slot
+// Persistent kernel, one CTA per SM, 18 warps:
+//   warp 0       TMA producer: weights once (cp.async.bulk), then the 4 KB point tiles through a 4-stage ring
+//   warp 1       MMA issuer (one elected thread), serves whichever of the two tile slots is ready
+//   warps 2-9    epilogue of slot 0   } each slot owns 256 TMEM columns and one activation buffer; while one
+//   warps 10-17  epilogue of slot 1   } slot's epilogue normalises layer k, the tensor core runs the other slot
 //
 // All operands use the no-swizzle K-major UMMA canonical layout (8x16B core matrices, LBO = 128 B
 // between K-adjacent cores, SBO = K*16 B between 8-row groups); the staging kernel and the weight
@@ -25,9 +25,27 @@
 namespace pcrl {
 namespace tc {
 
+// profiling knobs (tools/probe_fwd.py): knock out individual epilogue passes to attribute time.  0 in production.
+__device__ int g_dbg = 0;
+__device__ long long g_trace[3 * 1024];  // CTA 0, g_dbg bit 7: three tracer threads x 512 (event, clock) pairs
+__device__ int g_trace_n = 0;
+struct Tracer {  // register-resident cursor, plain stores: no atomics or round trips on the traced path
+  int region, n;
+  bool on;
+  __device__ __forceinline__ void operator()(int ev) {
+#ifdef PCRL_FWD_TRACE  // compiled out of production builds (tools/probe_fwd.py documents how to enable)
+    if (on && n < 512) {
+      g_trace[region * 1024 + 2 * n] = ev;
+      g_trace[region * 1024 + 2 * n + 1] = clock64();
+      ++n;
+    }
+#endif
+  }
+};
+
 constexpr int kStages = 4;
 constexpr int kTileBytes = 128 * 16 * 2;  // one X tile: 128 points x 16 bf16
-constexpr int kThreads = 320;
+constexpr int kThreads = 64 + 2 * 8 * 32;  // TMA warp + MMA warp + 2 slots x 8 epilogue warps
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -143,7 +161,7 @@ __device__ __forceinline__ void stats32(const uint32_t (&v)[32], float (&s)[4], 
 }
 
 struct SmemLayout {
-  uint32_t w0, w1, w2, prm, xst, act, wkey, bars, total;
+  uint32_t w0, w1, w2, prm, xst, act, wkey, stat, bars, total;
 };
 __host__ __device__ inline SmemLayout make_layout(int c1, int c2, int c3) {
   SmemLayout L;
@@ -157,6 +175,7 @@ __host__ __device__ inline SmemLayout make_layout(int c1, int c2, int c3) {
   const int kmax = c1 > c2 ? c1 : c2;
   L.act = o;  o += 2 * 128 * kmax * 2;
   L.wkey = o; o += 2 * 4 * c3 * 8;
+  L.stat = o; o += 2 * 2 * 128 * 8;  // per slot, per channel half: (sum, sumsq) of every row
   L.bars = o; o += 128;
   L.total = o;
   return L;
@@ -184,7 +203,7 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(BAR(9 + s), 1);
-      mbar_init(BAR(11 + s), 128);
+      mbar_init(BAR(11 + s), 256);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -229,6 +248,7 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
       // per-slot progress: tile index (s, s+2, ...), layer, and how many epilogue hand-offs were consumed.
       // The issuer polls both slots and launches whichever is ready, so a slow epilogue on one slot never
       // holds back the other slot's next layer.
+      Tracer trace{0, 0, (g_dbg & 128) && blockIdx.x == 0};
       int tile_i[2] = {0, 1}, layer[2] = {0, 0};
       uint32_t ph_act[2] = {0, 0};
       bool first[2] = {true, true};
@@ -246,12 +266,14 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
             if (!first[s] && !mbar_test(BAR(11 + s), ph_act[s] & 1)) continue;         // previous layer-2 accumulator drained?
             if (!first[s]) ph_act[s]++;
             first[s] = false;
+            trace(100 + s * 10 + 0);
             tc_fence_after();
             mma_bf16(d_tmem, make_desc(sbase + L.xst + st * kTileBytes, 256), make_desc(sbase + L.w0, 256), id0, 0);
             mma_commit(BAR(5 + st));
           } else {
             if (!mbar_test(BAR(11 + s), ph_act[s] & 1)) continue;                      // h_{layer-1} written?
             ph_act[s]++;
+            trace(100 + s * 10 + layer[s]);
             tc_fence_after();
             const int K = (layer[s] == 1) ? c1 : c2;
             const uint32_t wb = sbase + ((layer[s] == 1) ? L.w1 : L.w2);
@@ -260,19 +282,26 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
               mma_bf16(d_tmem, make_desc(act + ks * 256, K * 16), make_desc(wb + ks * 256, K * 16), idesc, ks > 0);
           }
           mma_commit(BAR(9 + s));
+          trace(200 + s * 10 + layer[s]);
           progressed = true;
           if (++layer[s] == 3) {
             layer[s] = 0;
             tile_i[s] += 2;
           }
         }
-        if (!progressed) __nanosleep(40);
+        if (!progressed && !(g_dbg & 16)) __nanosleep(40);
       }
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int s = (warp - 2) >> 2;       // slot
-    const int q = warp & 3;              // TMEM lane quadrant this warp may access
+    // 8 warps per slot: two warps share each TMEM lane quadrant (hardware rule: a warp reaches lanes
+    // 32*(warp%4)..+31) and split the channels in halves.  LayerNorm needs whole-row statistics, so the pair
+    // exchanges its partial (sum, sum of squares) through shared memory around a 64-thread named barrier.
+    // Four epilogue warps per SM sub-partition instead of two: the epilogue is instruction-issue bound.
+    const int ew = warp - 2;
+    const int s = ew >> 3;               // slot
+    const int h = (ew >> 2) & 1;         // which half of the channels this warp owns
+    const int q = warp & 3;              // TMEM lane quadrant
     const int row = q * 32 + lane;       // point within the tile
     const int kmax = c1 > c2 ? c1 : c2;
     unsigned char* act = smem + L.act + s * 128 * kmax * 2;
@@ -280,25 +309,52 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
     const float *g1 = prm, *be1 = prm + c2, *g2 = prm + 2 * c2, *be2 = prm + 2 * c2 + c3;
     unsigned long long* wkey = reinterpret_cast<unsigned long long*>(smem + L.wkey) + (s * 4 + q) * c3;
     const unsigned long long* wkey_slot = reinterpret_cast<unsigned long long*>(smem + L.wkey) + s * 4 * c3;
-    const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 256);
-    const int tid_slot = threadIdx.x - (64 + s * 128);
+    float2* stat_mine = reinterpret_cast<float2*>(smem + L.stat) + (s * 2 + h) * 128 + row;
+    const float2* stat_peer = reinterpret_cast<const float2*>(smem + L.stat) + (s * 2 + (h ^ 1)) * 128 + row;
+    const int pair_bar = 3 + s * 4 + q;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 256);
+    const int tid_slot = threadIdx.x - (64 + s * 256);
     uint32_t ph_acc = 0;
     mbar_wait(BAR(0), 0);  // LN parameters landed
+    const int dbg = g_dbg;
+    Tracer trace_e{1 + s, 0, (dbg & 128) && blockIdx.x == 0 && (ew & 7) == 0 && lane == 0};
+
+    // whole-row LayerNorm statistics from this warp's half [col0, col0 + ncols) plus the partner's partial
+    auto row_stats = [&](int col0, int ncols, int width, float& rstd, float& nmr) {
+      uint32_t v[32];
+      float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int ch = 0; ch < ncols; ch += 32) {
+        tmem_ld32(tlane + col0 + ch, v);
+        stats32(v, s4, q4);
+      }
+      float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]), sq = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+      *stat_mine = make_float2(sum, sq);
+      named_bar(pair_bar, 64);
+      const float2 o = *stat_peer;
+      sum += o.x;
+      sq += o.y;
+      const float mean = sum / (float)width;
+      const float var = fmaxf(sq / (float)width - mean * mean, 0.f);
+      rstd = rsqrtf(var + ln_eps);
+      nmr = -mean * rstd;
+    };
 
     for (int i = s; i < n_local; i += 2) {
       const int64_t tile = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
       const int cloud = (int)(tile / tiles_per_cloud);
-      uint32_t v[32], v2[32];
 
       // ---- layer 0: relu -> bf16 -> activation buffer (K = c1)
       mbar_wait(BAR(9 + s), ph_acc & 1);
       ph_acc++;
+      trace_e(300 + s * 10 + 0);
       tc_fence_after();
-      {
+      if (!(dbg & 64)) {
+        uint32_t v[32];
         const uint32_t sbo = (uint32_t)c1 * 16;
         unsigned char* dst = act + (row >> 3) * sbo + (row & 7) * 16;
-        for (int ch = 0; ch < c1; ch += 32) {
-          tmem_ld32(taddr0 + ch, v);
+        const int col0 = h * (c1 >> 1);
+        for (int ch = col0; ch < col0 + (c1 >> 1); ch += 32) {
+          tmem_ld32(tlane + ch, v);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 o;
@@ -313,31 +369,22 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
       fence_async_smem();
       tc_fence_before();
       mbar_arrive(BAR(11 + s));
+      trace_e(400 + s * 10 + 0);
 
-      // ---- layer 1: LN over channels (thread-local) + relu -> bf16 -> activation buffer (K = c2)
+      // ---- layer 1: LN over channels + relu -> bf16 -> activation buffer (K = c2)
       mbar_wait(BAR(9 + s), ph_acc & 1);
       ph_acc++;
+      trace_e(300 + s * 10 + 1);
       tc_fence_after();
-      {
-        float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
-        tmem_ld32_async(taddr0, v);
-        for (int ch = 0; ch < c2; ch += 64) {  // c2 % 64 == 0: two register buffers ping-pong
-          tmem_wait_ld();
-          tmem_ld32_async(taddr0 + ch + 32, v2);
-          stats32(v, s4, q4);
-          tmem_wait_ld();
-          if (ch + 64 < c2) tmem_ld32_async(taddr0 + ch + 64, v);
-          stats32(v2, s4, q4);
-        }
-        const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]), sq = (q4[0] + q4[1]) + (q4[2] + q4[3]);
-        const float mean = sum / (float)c2;
-        const float var = fmaxf(sq / (float)c2 - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + ln_eps);
-        const float nmr = -mean * rstd;
+      if (!(dbg & 32)) {
+        const int col0 = h * (c2 >> 1);
+        float rstd, nmr;
+        row_stats(col0, c2 >> 1, c2, rstd, nmr);
+        uint32_t v[32];
         const uint32_t sbo = (uint32_t)c2 * 16;
         unsigned char* dst = act + (row >> 3) * sbo + (row & 7) * 16;
-        for (int ch = 0; ch < c2; ch += 32) {
-          tmem_ld32(taddr0 + ch, v);
+        for (int ch = col0; ch < col0 + (c2 >> 1); ch += 32) {
+          tmem_ld32(tlane + ch, v);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float4 ga = *reinterpret_cast<const float4*>(g1 + ch + 8 * j);
@@ -361,38 +408,27 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
       fence_async_smem();
       tc_fence_before();
       mbar_arrive(BAR(11 + s));
+      trace_e(400 + s * 10 + 1);
 
-      // ---- layer 2: LN + relu, max (and argmax) over the tile's points
+      // ---- layer 2: LN, then max (and argmax) over the tile's points; ReLU is applied after the max
       mbar_wait(BAR(9 + s), ph_acc & 1);
       ph_acc++;
       tc_fence_after();
       {
-        float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
-        tmem_ld32_async(taddr0, v);
-        for (int ch = 0; ch < c3; ch += 64) {
-          tmem_wait_ld();
-          tmem_ld32_async(taddr0 + ch + 32, v2);
-          stats32(v, s4, q4);
-          tmem_wait_ld();
-          if (ch + 64 < c3) tmem_ld32_async(taddr0 + ch + 64, v);
-          stats32(v2, s4, q4);
-        }
-        const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]), sq = (q4[0] + q4[1]) + (q4[2] + q4[3]);
-        const float mean = sum / (float)c3;
-        const float var = fmaxf(sq / (float)c3 - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + ln_eps);
-        const float nmr = -mean * rstd;
-        named_bar(1 + s, 128);  // previous tile's combine has finished reading wkey
+        const int col0 = h * (c3 >> 1);
+        float rstd = 1.f, nmr = 0.f;
+        if (!(dbg & 4)) row_stats(col0, c3 >> 1, c3, rstd, nmr);
+        if (dbg & 2) row_stats(col0, c3 >> 1, c3, rstd, nmr);
+        named_bar(1 + s, 256);  // previous tile's combine has finished reading wkey
         // Max over the warp's 32 points per channel without cross-lane reductions: every lane packs
-        // (value bits & ~31) | (31 - lane) -- post-ReLU floats are non-negative so the bit pattern is
-        // order-preserving, and the low 5 mantissa bits carry the lane so ties resolve to the smallest
-        // point index -- writes its 32 keys as one row of a warp-private 32x32 tile (XOR-swizzled float4
-        // chunks, conflict-free) in the slot's idle activation buffer, then reads back one COLUMN.
-        uint32_t* tr = reinterpret_cast<uint32_t*>(act) + q * 1024;  // 4 KB per warp
+        // (value bits & ~31) | (31 - lane) -- the low 5 mantissa bits carry the lane so ties resolve to the
+        // smallest point index -- writes its 32 keys as one row of a warp-private 32x32 tile (XOR-swizzled
+        // float4 chunks, conflict-free) in the slot's idle activation buffer, then reads back one COLUMN.
         // Padding rows (n >= N) are staged as copies of the cloud's point 0, so they can only tie with a
         // real point and the smallest-index rule drops them: no masking.  ReLU commutes with max, so it is
         // applied once per (cloud, channel) in the finalize kernel; here keys are compared as SIGNED ints
         // (any positive float beats any negative one; the order among negatives is irrelevant after ReLU).
+        uint32_t* tr = reinterpret_cast<uint32_t*>(act) + (h * 4 + q) * 1024;  // 4 KB per warp
         const uint32_t lane_tag = 31u - (uint32_t)lane;
         uint32_t st_off[8], ld_off[8];  // XOR-swizzled word offsets, hoisted out of the chunk loop
 #pragma unroll
@@ -400,8 +436,10 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
           st_off[k] = (uint32_t)(lane * 32 + ((k ^ (lane & 7)) << 2));
           ld_off[k] = (uint32_t)((((lane >> 2) ^ k) << 2) + (lane & 3));
         }
-        auto reduce_chunk = [&](const uint32_t (&y)[32], int ch) {
-          uint32_t key[32];
+        uint32_t v[32];
+        for (int ch = col0; ch < col0 + (c3 >> 1); ch += 32) {
+          if (dbg & 1) break;
+          tmem_ld32(tlane + ch, v);
 #pragma unroll
           for (int j4 = 0; j4 < 32; j4 += 4) {
             const float4 gg = *reinterpret_cast<const float4*>(g2 + ch + j4);
@@ -409,15 +447,14 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
             const float gv[4] = {gg.x, gg.y, gg.z, gg.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float o = fmaf(fmaf(__uint_as_float(y[j4 + e]), rstd, nmr), gv[e], bv[e]);
-              key[j4 + e] = (__float_as_uint(o) & ~31u) | lane_tag;
+              const float o = fmaf(fmaf(__uint_as_float(v[j4 + e]), rstd, nmr), gv[e], bv[e]);
+              v[j4 + e] = (__float_as_uint(o) & ~31u) | lane_tag;
             }
           }
           __syncwarp();  // previous chunk's column reads are done
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4)
-            *reinterpret_cast<uint4*>(tr + st_off[c4]) =
-                make_uint4(key[4 * c4], key[4 * c4 + 1], key[4 * c4 + 2], key[4 * c4 + 3]);
+            *reinterpret_cast<uint4*>(tr + st_off[c4]) = make_uint4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
           __syncwarp();
           int m0 = INT_MIN, m1 = INT_MIN;  // two independent max chains
 #pragma unroll
@@ -430,20 +467,11 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
           // turns the signed order into an unsigned one for the packed u64 atomicMax across warps / tiles.
           const uint32_t idx = (uint32_t)((int)(tile % tiles_per_cloud) * 128 + q * 32) + (31u - (m & 31u));
           wkey[ch + lane] = ((unsigned long long)((m & ~31u) ^ 0x80000000u) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
-        };
-        tmem_ld32_async(taddr0, v);
-        for (int ch = 0; ch < c3; ch += 64) {
-          tmem_wait_ld();
-          tmem_ld32_async(taddr0 + ch + 32, v2);
-          reduce_chunk(v, ch);
-          tmem_wait_ld();
-          if (ch + 64 < c3) tmem_ld32_async(taddr0 + ch + 64, v);
-          reduce_chunk(v2, ch + 32);
         }
         tc_fence_before();
         mbar_arrive(BAR(11 + s));  // accumulator drained: the MMA warp may start this slot's next tile
-        named_bar(1 + s, 128);
-        for (int c = tid_slot; c < c3; c += 128) {
+        named_bar(1 + s, 256);
+        for (int c = tid_slot; c < c3; c += 256) {
           unsigned long long k = wkey_slot[c];
           k = max(k, wkey_slot[c3 + c]);
           k = max(k, wkey_slot[2 * c3 + c]);
@@ -514,8 +542,9 @@ __global__ void pack_weights_kernel(const float* __restrict__ w0, const float* _
 
 static bool shapes_ok(int c1, int c2, int c3) {
   auto ok = [](int c, int m) { return c >= m && c <= 256 && c % m == 0; };
-  // activation buffer doubles as the 16 KB max-pool transpose scratch: needs max(c1, c2) >= 64
-  return ok(c1, 32) && ok(c2, 64) && ok(c3, 64) && (c1 >= 64 || c2 >= 64) && make_layout(c1, c2, c3).total <= 227 * 1024;
+  // every layer's channels split into two halves of whole 32-column chunks; the activation buffer doubles as
+  // the 32 KB max-pool transpose scratch (8 warps x 4 KB): needs max(c1, c2) >= 128
+  return ok(c1, 64) && ok(c2, 64) && ok(c3, 64) && (c1 >= 128 || c2 >= 128) && make_layout(c1, c2, c3).total <= 227 * 1024;
 }
 
 }  // namespace tc
@@ -524,6 +553,20 @@ static bool shapes_ok(int c1, int c2, int c3) {
 using namespace pcrl;
 
 extern "C" {
+
+// not part of the public header: profiling switches for tools/probe_fwd.py
+int pcrl_debug_set_fwd_flags(int flags) {
+  int zero = 0;
+  PCRL_CHECK_CUDA(cudaMemcpyToSymbol(tc::g_dbg, &flags, sizeof(int)));
+  PCRL_CHECK_CUDA(cudaMemcpyToSymbol(tc::g_trace_n, &zero, sizeof(int)));
+  static long long zeros[3 * 1024] = {0};
+  PCRL_CHECK_CUDA(cudaMemcpyToSymbol(tc::g_trace, zeros, sizeof(zeros)));
+  return PCRL_OK;
+}
+int pcrl_debug_get_trace(long long* out_host, int max_events) {
+  PCRL_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, tc::g_trace, sizeof(long long) * 3 * 1024));
+  return 3 * 512;
+}
 
 int64_t pcrl_pointnet_wpack_bytes(int c1, int c2, int c3) {
   return (int64_t)c1 * 32 + (int64_t)c2 * c1 * 2 + (int64_t)c3 * c2 * 2 + (2 * c2 + 2 * c3) * 4;
