@@ -235,8 +235,7 @@ def native_arm(args, w, rank, world, local_rank):
         eng.update(2)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
 
     # ---- device-resident throughput (`value`)
@@ -283,8 +282,7 @@ def native_arm(args, w, rank, world, local_rank):
     dev_ms, e2e_ms = [float(x) for x in times.tolist()]
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
 
     # ---- roofline of the dominant kernel (rank 0, kernel alone, L2 flushed between launches)
@@ -334,8 +332,17 @@ def native_arm(args, w, rank, world, local_rank):
         "roofline": roofline, "cpu_baseline": cpu, "last_scalars": {k: round(v, 5) for k, v in ret.items()},
     }
     print(json.dumps(line), flush=True)
+    _finish(world)
+
+
+def _finish(world):
+    """Multi-rank exit: tearing the NCCL communicator down while captured CUDA graphs still reference its kernels
+    can block forever, so ranks just flush and leave (exit code 0) once their own work is done."""
     if world > 1:
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 def main():
