@@ -15,8 +15,10 @@ def attach(engine, group=None):
     world = dist.get_world_size(group)
     engine.world_size = world
 
-    def allreduce(flat_grad: torch.Tensor):
-        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+    def allreduce(flat_grad: torch.Tensor, async_op: bool = False):
+        """SUM over ranks (1/world is folded into the fused Adam).  async_op=True returns a work handle: NCCL runs on
+        its own stream and `handle.wait()` re-joins the compute stream, so the reduce overlaps later kernels."""
+        return dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
     engine.allreduce = allreduce if world > 1 else None
     return engine
