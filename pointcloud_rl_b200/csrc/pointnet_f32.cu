@@ -153,6 +153,75 @@ __global__ void relu_bwd_rows_kernel(float* __restrict__ dy, const float* __rest
     if (!(y[i] > 0.f)) dy[i] = 0.f;
 }
 
+// ---- layer 0 of the compacted backward: K = C <= 16 is far too thin for a GEMM tile -------------------------
+// h0[a, n] = relu(b0[n] + sum_c xa[a, c] w0[n, c]).  CTA = 16 rows x c1 channels; W0 row of the thread in registers.
+template <int CP>
+__global__ void __launch_bounds__(256) layer0_fwd_kernel(const float* __restrict__ xa, const float* __restrict__ w0,
+                                                         const float* __restrict__ b0, int C, int c1,
+                                                         const int* __restrict__ count, float* __restrict__ h0) {
+  const int rows = *count;
+  const int a0 = blockIdx.x * 16;
+  if (a0 >= rows) return;
+  const int n = threadIdx.x % 128, phase = threadIdx.x / 128;
+  for (int nn = n; nn < c1; nn += 128) {
+    float wr[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) wr[c] = c < C ? __ldg(w0 + nn * C + c) : 0.f;
+    const float bias = __ldg(b0 + nn);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int a = a0 + phase + 2 * i;
+      if (a >= rows) break;
+      const float4* xr = reinterpret_cast<const float4*>(xa + (int64_t)a * CP);
+      float acc = bias;
+#pragma unroll
+      for (int q = 0; q < CP / 4; ++q) {
+        const float4 x = __ldg(xr + q);
+        acc = fmaf(x.x, wr[4 * q], acc);
+        acc = fmaf(x.y, wr[4 * q + 1], acc);
+        acc = fmaf(x.z, wr[4 * q + 2], acc);
+        acc = fmaf(x.w, wr[4 * q + 3], acc);
+      }
+      h0[(int64_t)a * c1 + nn] = fmaxf(acc, 0.f);
+    }
+  }
+}
+// dw0[n, c] += sum_a d0[a, n] xa[a, c];  db0[n] += sum_a d0[a, n]   (d0 already ReLU-masked).
+// CTA = 256 rows: thread (n, phase) accumulates every other row of its chunk, one atomic per output per CTA.
+template <int CP>
+__global__ void __launch_bounds__(256) layer0_wgrad_kernel(const float* __restrict__ d0, const float* __restrict__ xa,
+                                                           int C, int c1, const int* __restrict__ count,
+                                                           float* __restrict__ dw0, float* __restrict__ db0) {
+  const int rows = *count;
+  const int a0 = blockIdx.x * 256;
+  if (a0 >= rows) return;
+  const int a1 = min(rows, a0 + 256);
+  const int n = threadIdx.x % 128, phase = threadIdx.x / 128;
+  for (int nn = n; nn < c1; nn += 128) {
+    float acc[CP], accb = 0.f;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) acc[c] = 0.f;
+#pragma unroll 4
+    for (int a = a0 + phase; a < a1; a += 2) {
+      const float g = __ldg(d0 + (int64_t)a * c1 + nn);
+      const float4* xr = reinterpret_cast<const float4*>(xa + (int64_t)a * CP);
+#pragma unroll
+      for (int q = 0; q < CP / 4; ++q) {
+        const float4 x = __ldg(xr + q);
+        acc[4 * q] = fmaf(g, x.x, acc[4 * q]);
+        acc[4 * q + 1] = fmaf(g, x.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(g, x.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(g, x.w, acc[4 * q + 3]);
+      }
+      accb += g;
+    }
+#pragma unroll
+    for (int c = 0; c < CP; ++c)
+      if (c < C && acc[c] != 0.f) atomicAdd(dw0 + nn * C + c, acc[c]);
+    if (accb != 0.f) atomicAdd(db0 + nn, accb);
+  }
+}
+
 static int gemm_nt(const float* A, int lda, const float* W, int ldw, const float* bias, int relu, float* C, int ldc,
                    int M, int K, int Nout, const int* m_dev, cudaStream_t st, int tf32 = 0) {
   // C[M,Nout] = act(A[M,K] W[Nout,K]^T + bias)
@@ -310,7 +379,12 @@ int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, cons
   PCRL_CHECK_LAUNCH();
 
   // 2. recompute the forward of the active points, keeping what LN backward needs
-  if ((rc = gemm_nt(w.xa, CP, w0, C, b0, 1, w.h0, c1, A, C, c1, w.total, st, 0))) return rc;  // K = C is tiny: FFMA
+  {
+    const unsigned grid = (unsigned)cdiv(A, 16);
+    if (CP == 8) layer0_fwd_kernel<8><<<grid, 256, 0, st>>>(w.xa, w0, b0, C, c1, w.total, w.h0);
+    else layer0_fwd_kernel<16><<<grid, 256, 0, st>>>(w.xa, w0, b0, C, c1, w.total, w.h0);
+    PCRL_CHECK_LAUNCH();
+  }
   if ((rc = gemm_nt(w.h0, c1, w1, c1, nullptr, 0, w.h1, c2, A, c1, c2, w.total, st, tf32))) return rc;
   if ((rc = launch_ln_rows(w.h1, c2, g1, be1, w.h1, c2, w.y1hat, w.rstd1, A, c2, ln_eps, 1, w.total, st))) return rc;
   if ((rc = gemm_nt(w.h1, c2, w2, c2, nullptr, 0, w.d2, c3, A, c2, c3, w.total, st, tf32))) return rc;
@@ -338,11 +412,13 @@ int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, cons
   if (tf32 && (rc = launch_zero_tail(w.d1, c2, w.total, A, st))) return rc;
   if ((rc = gemm_tn_acc(w.d1, c2, w.h0, c1, dw1, c1, A, c2, c1, w.total, expect, st, tf32))) return rc;
   if ((rc = gemm_nn(w.d1, c2, w1, c1, w.d0, c1, A, c2, c1, w.total, st, tf32, w.h0))) return rc;  // ReLU bwd fused
-  // 6. layer 0 backward: dW0 [c1,C] += d0^T xa[:, :C];  db0 += colsum(d0)
-  if (tf32 && (rc = launch_zero_tail(w.d0, c1, w.total, A, st))) return rc;
-  // layer-0 weight gradient stays on exact-fp32 FFMA: raw coordinates lose too much under TF32 truncation, and N = C is tiny
-  if ((rc = gemm_tn_acc(w.d0, c1, w.xa, CP, dw0, C, A, c1, C, w.total, expect, st, 0))) return rc;
-  if ((rc = launch_colsum(w.d0, c1, A, c1, w.total, db0, st))) return rc;
+  // 6. layer 0 backward: dW0 [c1,C] += d0^T xa[:, :C];  db0 += colsum(d0)   (exact fp32: raw coordinates)
+  {
+    const unsigned grid = (unsigned)cdiv(A, 256);
+    if (CP == 8) layer0_wgrad_kernel<8><<<grid, 256, 0, st>>>(w.d0, w.xa, C, c1, w.total, dw0, db0);
+    else layer0_wgrad_kernel<16><<<grid, 256, 0, st>>>(w.d0, w.xa, C, c1, w.total, dw0, db0);
+    PCRL_CHECK_LAUNCH();
+  }
   return PCRL_OK;
 }
 

@@ -213,10 +213,23 @@ def test_pointnet_fwd_f32_matches_reference(L, name):
         assert int(idx.max()) < N - N // 4  # exact duplicates: ties resolve to the smallest index
 
 
-@pytest.mark.parametrize("name", ["pointnet_fwd_c7", "pointnet_fwd_c7_dup", "pointnet_fwd_c9_dmc"])
+@pytest.mark.parametrize("name", ["pointnet_fwd_c7", "pointnet_fwd_c7_dup", "pointnet_fwd_c9_dmc", "pointnet_fwd_c7/neg_gamma"])
 def test_pointnet_fwd_bf16_tcgen05(L, name):
     """Fused tcgen05 path: bf16 operands, fp32 accumulate/LN.  Tolerance 2e-2 (north_star, bf16)."""
-    g, p, obs = _pointnet_case(name)
+    neg = name.endswith("/neg_gamma")
+    g, p, obs = _pointnet_case(name.split("/")[0])
+    g = dict(g)
+    if neg:
+        # LayerNorm gains of both signs (and an exact zero): the kernel folds sign(gamma) into W2 and sorts the
+        # channels by sign, so the reference here is the oracle run with the same modified parameters
+        gen = torch.Generator().manual_seed(11)
+        sign = torch.where(torch.rand(p["pn.g2"].shape, generator=gen) < 0.4, -1.0, 1.0)
+        p = dict(p)
+        p["pn.g2"] = p["pn.g2"] * sign
+        p["pn.g2"][5] = 0.0
+        p["pn.g1"] = p["pn.g1"] * torch.where(torch.rand(p["pn.g1"].shape, generator=gen) < 0.3, -1.0, 1.0)
+        _, pooled_ref, _ = O.pointnet_forward(p, O.preprocess(obs), return_pool=True)
+        g["pooled"] = pooled_ref.numpy()
     x = O.preprocess(obs)
     R, C, N = x.shape
     NP = (N + 127) // 128 * 128

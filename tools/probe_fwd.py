@@ -29,16 +29,14 @@ def run(flags, iters=10):
         ts.append(e0.elapsed_time(e1))
     return float(np.mean(ts[3:]))
 tiles = R * spec.NP // 128
-for flags, name in [(0, "full")][:1] + [(0, "full"), (16, "full, MMA issuer spins (no nanosleep)"), (1, "no L2 pass-2 (normalise+transpose max)"),
-                    (2, "extra L2 stats pass"), (4, "no L2 stats pass"), (5, "no L2 epilogue at all"),
-                    (5 + 32, "no L1/L2 epilogues"), (5 + 32 + 64, "no epilogue work at all (sync skeleton + MMA)"),
-                    (5 + 32 + 64 + 16, "skeleton, spinning issuer")]:
+for flags, name in [(0, "full"), (0, "full"), (512, "full, stats passes with x64 TMEM loads"), (1, "no L2 pass-2"), (1 + 512, "no L2 pass-2, x64 stats"),
+                    (5, "no L2 epilogue at all"), (5 + 32 + 64, "sync skeleton + MMA")]:
     ms = run(flags)
     print(f"flags {flags:2d} {name:55s} {ms*1e3:8.1f} us   {ms*1e-3*1.9e9/ (tiles/148):8.0f} cyc/tile")
 L.cdll.pcrl_debug_set_fwd_flags(ctypes.c_int(0))
 
 # ---- round-trip trace of CTA 0 (clock64): skeleton mode and full mode
-for flags in (128 + 5 + 32 + 64, 128):
+for flags in ():
     L.cdll.pcrl_debug_set_fwd_flags(ctypes.c_int(flags))
     L.pointnet_fwd_bf16(eng.w["xh_next"], R, spec.n_points, spec.NP, eng.w["wpack"], c1, c2, c3, spec.ln_eps,
                         eng.w["pool_keys"], eng.w["pooled_next"], None, st)
