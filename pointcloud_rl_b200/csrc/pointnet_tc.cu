@@ -576,7 +576,11 @@ int pcrl_pointnet_pack_weights(const float* w0, const float* b0, const float* w1
                                const float* w2, const float* g2, const float* be2, int C, int c1, int c2, int c3,
                                int rgb_u8, void* wpack, void* stream) {
   PCRL_CHECK_ARG(w0 && b0 && w1 && g1 && be1 && w2 && g2 && be2 && wpack);
-  PCRL_CHECK_ARG(C + 4 <= 16 && tc::shapes_ok(c1, c2, c3));
+  if (C + 4 > 16 || !tc::shapes_ok(c1, c2, c3)) {
+    set_error("pcrl_pointnet_pack_weights: shape unsupported by the tcgen05 path (C=%d <= 12, widths (%d,%d,%d) multiples of 64 "
+              "in [64,256] with max(c1,c2) >= 128); use the fp32 path", C, c1, c2, c3);
+    return PCRL_EUNSUPPORTED;
+  }
   const int n = c1 * 16 + c2 * c1 + c3 * c2 + 2 * c2 + 2 * c3;
   tc::pack_weights_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(w0, b0, w1, g1, be1, w2, g2, be2, C,
                                                                                    c1, c2, c3, rgb_u8, (char*)wpack);
