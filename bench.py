@@ -182,7 +182,7 @@ def time_dominant_kernel(eng, spec, w, iters=20):
         e0.record()
         if eng.precision == "bf16":
             L.pointnet_fwd_bf16(eng.w["xh_next"], R, spec.n_points, spec.NP, eng.w["wpack"], c1, c2, c3, spec.ln_eps,
-                                eng.w["pool_keys"], eng.w["pooled_next"], None, st)
+                                eng.w["pool_keys_next"], eng.w["pooled_next"], None, st)
         else:
             p = eng.p
             L.pointnet_fwd_f32(eng.w["xf_next"], R, spec.n_points, spec.NP, spec.CP, spec.C, p["pn.w0"], p["pn.b0"],

@@ -221,11 +221,12 @@ class UpdateEngine:
         w["dout"] = torch.zeros(B, 2 * A, **f32)
         w["dlog_alpha"] = self.g["log_alpha"]
         # MLP activations: [net][layer]; no-grad passes reuse "tmp"
-        for net in ("tmp", "q0", "q1", "actor"):
+        for net in ("tmp", "tmp2", "q0", "q1", "actor"):
             w[f"h1_{net}"] = torch.zeros(R, h1, **f32)
             w[f"h2_{net}"] = torch.zeros(R, h2, **f32)
-        w["dh1"] = torch.zeros(R, h1, **f32)
-        w["dh2"] = torch.zeros(R, h2, **f32)
+        for sc in ("a", "b"):  # backward scratch of the two Q heads, which run on parallel streams
+            w[f"dh1_{sc}"] = torch.zeros(R, h1, **f32)
+            w[f"dh2_{sc}"] = torch.zeros(R, h2, **f32)
         w["dx0"] = torch.zeros(R, D + S + A, **f32)
         w["dx1"] = torch.zeros(R, D + S + A, **f32)
         chunk = max(1, min(R, fwd_chunk_clouds))
@@ -234,10 +235,12 @@ class UpdateEngine:
         w["scratch"] = torch.zeros(max(self.fwd_ws_bytes, self.bwd_ws_bytes), dtype=torch.uint8, device=dev)
         if bf16:
             w["wpack"] = torch.zeros(int(self.L.pointnet_wpack_bytes(c1, c2, c3)), dtype=torch.uint8, device=dev)
-            w["pool_keys"] = torch.zeros(R * c3, dtype=torch.int64, device=dev)
+            for name in ("next", "obs", "pi"):
+                w[f"pool_keys_{name}"] = torch.zeros(R * c3, dtype=torch.int64, device=dev)
         self.w = w
         self._graphs = {}
         self.graph_calls = {}
+        self._side = [torch.cuda.Stream(device=dev) for _ in range(3)] if dev.type == "cuda" else []
         self._landing = None
 
     # ------------------------------------------------------------------ parameters
@@ -315,7 +318,7 @@ class UpdateEngine:
         argmax = w["argmax_obs"] if want_argmax else None
         if self.precision == "bf16":
             self.L.pointnet_fwd_bf16(w[f"xh_{name}"], rows, sp.n_points, sp.NP, w["wpack"], c1, c2, c3, sp.ln_eps,
-                                     w["pool_keys"], w[f"pooled_{name}"], argmax, st)
+                                     w[f"pool_keys_{name}"], w[f"pooled_{name}"], argmax, st)
         else:
             self.L.pointnet_fwd_f32(w[f"xf_{name}"], rows, sp.n_points, sp.NP, sp.CP, sp.C, p["pn.w0"], p["pn.b0"],
                                     p["pn.w1"], p["pn.g1"], p["pn.be1"], p["pn.w2"], p["pn.g2"], p["pn.be2"], c1, c2,
@@ -346,9 +349,10 @@ class UpdateEngine:
         self.L.linear_fwd(h1, h1n, p[f"{net}.w1"], p[f"{net}.b1"], h2, h2n, M, h1n, h2n, 1, self.tf32, st)
         self.L.linear_fwd(h2, h2n, p[f"{net}.w2"], p[f"{net}.b2"], out, ldo, M, h2n, nout, 0, self.tf32, st)
 
-    def _mlp_bwd(self, net, x, K, M, dout, lddo, nout, keep, dx, want_w, st):
-        p, g, w, (h1n, h2n) = self.p, self.g, self.w, self.spec.hidden
-        h1, h2 = w[f"h1_{keep}"], w[f"h2_{keep}"]
+    def _mlp_bwd(self, net, x, K, M, dout, lddo, nout, keep, dx, want_w, st, scratch="a"):
+        p, g, (h1n, h2n) = self.p, self.g, self.spec.hidden
+        h1, h2 = self.w[f"h1_{keep}"], self.w[f"h2_{keep}"]
+        w = {"dh1": self.w[f"dh1_{scratch}"], "dh2": self.w[f"dh2_{scratch}"]}
         gw = (lambda n: g[f"{net}.{n}"]) if want_w else (lambda n: None)
         # each layer's dX GEMM applies the previous ReLU's backward in its epilogue (mask = saved post-activation)
         self.L.linear_bwd(h2, h2n, p[f"{net}.w2"], dout, lddo, gw("w2"), gw("b2"), w["dh2"], h2n, h2, h2n, M, h2n, nout,
@@ -372,11 +376,26 @@ class UpdateEngine:
                          pb, pe, float(hp.tau), st)
 
     # ------------------------------------------------------------------ the update
+    # ------------------------------------------------------------------ stream forks
+    def _fork(self, idx):
+        """Side stream `idx`, ordered after everything enqueued so far on the current stream.  Independent chains of
+        the update (target branch vs critic forward, the two Q heads) run on forked streams: most of their kernels
+        fill only part of the 148 SMs, and inside a CUDA graph the forks become parallel branches."""
+        side = self._side[idx]
+        side.wait_stream(torch.cuda.current_stream())
+        return side
+
+    @staticmethod
+    def _join(*sides):
+        cur = torch.cuda.current_stream()
+        for s_ in sides:
+            cur.wait_stream(s_)
+
     def update(self, updates: int, noise: Optional[Dict[str, torch.Tensor]] = None):
         """Enqueues one full update on the current stream.  `noise` (parity mode) injects the reference's
         random draws: jitter_obs/jitter_next or angle_obs/angle_next, eps_next, eps_pi (device tensors)."""
         sp, hp, w, p, L = self.spec, self.hp, self.w, self.p, self.L
-        st = stream_ptr()
+        ST = stream_ptr  # evaluated at every call site: forked sections run on their own stream
         B, R, k = self.B, self.R, self.k
         D, S, A = sp.out_dim, sp.state_dim, sp.action_dim
         c1, c2, c3 = sp.widths
@@ -388,94 +407,112 @@ class UpdateEngine:
         ld_cat = D + S + A
         target_entropy = float(hp.target_entropy) if hp.target_entropy is not None else -float(A)
 
-        self._pack_weights(st)
-        # ---- staging (+ augmentation fused into the load)
-        self._stage("next_obs", "next", k, aug, noise.get(f"{nkey}_next") if nkey else None, 1, st)
-        self._stage("obs", "obs", k, aug, noise.get(f"{nkey}_obs") if nkey else None, 0, st)
+        self._pack_weights(ST())
 
-        # ---- TD target (no grad): sac.py:108-134 / drq.py:71-87
-        self._encode("next", R, False, st)
-        cat = w["cat_next"]
-        if S:
-            L.copy_cols(self.raw["next_obs"]["state"], S, k, 1, cat, ld_cat, D, R, S, st)
-        self._mlp_fwd("actor", cat, D + S, R, w["out_next"], 2 * A, 2 * A, "tmp", st)
-        L.tanh_gaussian_fwd(w["out_next"], R, A, hp.log_std_bound[0], hp.log_std_bound[1], hp.head_scale, hp.head_bias,
-                            noise.get("eps_next"), self.seed, self.counter, 2, cat[:, D + S:], ld_cat, w["nlp_next"],
-                            w["eps_next"], st)
-        self._mlp_fwd("tq0", cat, ld_cat, R, w["q_next"], 2, 1, "tmp", st)
-        self._mlp_fwd("tq1", cat, ld_cat, R, w["q_next"][:, 1:], 2, 1, "tmp", st)
-        L.td_target(w["q_next"], w["nlp_next"], self.raw["rewards"], self.raw["dones"], B, k, hp.gamma,
-                    1.0 if hp.algo == "drq" else hp.reward_scale, int(hp.ignore_dones), self.alpha_dev, w["y"], st)
+        # ---- branch T (side stream 0): TD target, no grad -- sac.py:108-134 / drq.py:71-87
+        s_t = self._fork(0)
+        with torch.cuda.stream(s_t):
+            self._stage("next_obs", "next", k, aug, noise.get(f"{nkey}_next") if nkey else None, 1, ST())
+            self._encode("next", R, False, ST())
+            cat = w["cat_next"]
+            if S:
+                L.copy_cols(self.raw["next_obs"]["state"], S, k, 1, cat, ld_cat, D, R, S, ST())
+            self._mlp_fwd("actor", cat, D + S, R, w["out_next"], 2 * A, 2 * A, "tmp", ST())
+            L.tanh_gaussian_fwd(w["out_next"], R, A, hp.log_std_bound[0], hp.log_std_bound[1], hp.head_scale,
+                                hp.head_bias, noise.get("eps_next"), self.seed, self.counter, 2, cat[:, D + S:], ld_cat,
+                                w["nlp_next"], w["eps_next"], ST())
+            s_t1 = self._fork(1)
+            with torch.cuda.stream(s_t1):
+                self._mlp_fwd("tq1", cat, ld_cat, R, w["q_next"][:, 1:], 2, 1, "tmp2", ST())
+            self._mlp_fwd("tq0", cat, ld_cat, R, w["q_next"], 2, 1, "tmp", ST())
+            self._join(s_t1)
+            L.td_target(w["q_next"], w["nlp_next"], self.raw["rewards"], self.raw["dones"], B, k, hp.gamma,
+                        1.0 if hp.algo == "drq" else hp.reward_scale, int(hp.ignore_dones), self.alpha_dev, w["y"], ST())
 
-        # ---- critic step: sac.py:136-148 / drq.py:89-101
-        self._encode("obs", R, True, st)
+        # ---- critic forward on the main stream: sac.py:136 / drq.py:89
+        self._stage("obs", "obs", k, aug, noise.get(f"{nkey}_obs") if nkey else None, 0, ST())
+        self._encode("obs", R, True, ST())
         cat = w["cat_obs"]
         if S:
-            L.copy_cols(self.raw["obs"]["state"], S, k, 1, cat, ld_cat, D, R, S, st)
-        L.copy_cols(self.raw["actions"], A, k, 1, cat, ld_cat, D + S, R, A, st)
-        self._mlp_fwd("q0", cat, ld_cat, R, w["q_obs"], 2, 1, "q0", st)
-        self._mlp_fwd("q1", cat, ld_cat, R, w["q_obs"][:, 1:], 2, 1, "q1", st)
-        L.critic_loss(w["q_obs"], w["y"], R, w["dq"], self.scalars, st)
+            L.copy_cols(self.raw["obs"]["state"], S, k, 1, cat, ld_cat, D, R, S, ST())
+        L.copy_cols(self.raw["actions"], A, k, 1, cat, ld_cat, D + S, R, A, ST())
         c_lo, c_hi = self.layout.group_range["critic"]
         self.grads[c_lo:c_hi].zero_()
-        self._mlp_bwd("q0", cat, ld_cat, R, w["dq"], 2, 1, "q0", w["dx0"], True, st)
-        self._mlp_bwd("q1", cat, ld_cat, R, w["dq"][:, 1:], 2, 1, "q1", w["dx1"], True, st)
+        s_q = self._fork(2)
+        with torch.cuda.stream(s_q):
+            self._mlp_fwd("q1", cat, ld_cat, R, w["q_obs"][:, 1:], 2, 1, "q1", ST())
+        self._mlp_fwd("q0", cat, ld_cat, R, w["q_obs"], 2, 1, "q0", ST())
+        self._join(s_q, s_t)
+        L.critic_loss(w["q_obs"], w["y"], R, w["dq"], self.scalars, ST())
+
+        # ---- critic backward: the two heads in parallel, their feature gradients add (sac.py:141-142)
+        s_q = self._fork(2)
+        with torch.cuda.stream(s_q):
+            self._mlp_bwd("q1", cat, ld_cat, R, w["dq"][:, 1:], 2, 1, "q1", w["dx1"], True, ST(), "b")
+        self._mlp_bwd("q0", cat, ld_cat, R, w["dq"], 2, 1, "q0", w["dx0"], True, ST(), "a")
+        self._join(s_q)
         q_pending = None
         if self.allreduce is not None:
             # the two Q heads' gradients (97 % of the critic bytes) are final here: reduce them on NCCL's stream
             # while the PointNet head + sparse backward still run on the compute stream
             q_lo, q_hi = self.layout.q_range
             q_pending = self.allreduce(self.grads[c_lo + q_lo:c_lo + q_hi], async_op=True)
-        L.add_cols(w["dx0"], ld_cat, w["dx1"], ld_cat, w["dz"], D, R, D, st)  # both heads' d/dfeature add up
+        L.add_cols(w["dx0"], ld_cat, w["dx1"], ld_cat, w["dz"], D, R, D, ST())  # both heads' d/dfeature add up
         L.layernorm_bwd(w["dz"], D, w["xhat_obs"], w["rstd_obs"], p["pn.gf"], self.g["pn.gf"], self.g["pn.bef"],
-                        w["dz"], R, D, st)
+                        w["dz"], R, D, ST())
         L.linear_bwd(w["pooled_obs"], c3, p["pn.wf"], w["dz"], D, self.g["pn.wf"], self.g["pn.bf"], w["dpooled"], c3,
-                     None, 0, R, c3, D, self.tf32, st)
+                     None, 0, R, c3, D, self.tf32, ST())
         g = self.g
         L.pointnet_bwd(w["xf_obs"], R, sp.n_points, sp.NP, sp.CP, sp.C, w["pooled_obs"], w["argmax_obs"], w["dpooled"],
                        p["pn.w0"], p["pn.b0"], p["pn.w1"], p["pn.g1"], p["pn.be1"], p["pn.w2"], p["pn.g2"],
                        p["pn.be2"], c1, c2, c3, sp.ln_eps, g["pn.w0"], g["pn.b0"], g["pn.w1"], g["pn.g1"], g["pn.be1"],
-                       g["pn.w2"], g["pn.g2"], g["pn.be2"], w["scratch"], self.bwd_ws_bytes, self.tf32, st)
+                       g["pn.w2"], g["pn.g2"], g["pn.be2"], w["scratch"], self.bwd_ws_bytes, self.tf32, ST())
         if self.allreduce is not None:
             self.allreduce(self.grads[c_lo:c_lo + self.layout.q_range[0]])  # PointNet gradients (0.3 MB)
             q_pending.wait()
-        self._adam("critic", 0, hp.lr, hp.betas, 4, do_target, st)  # + Polyak fused (sac.py:207-208)
+        self._adam("critic", 0, hp.lr, hp.betas, 4, do_target, ST())  # + Polyak fused (sac.py:207-208)
 
         # ---- actor + alpha step: sac.py:161-205 / drq.py:114-155
         if do_actor:
             if k > 1:  # first augmentation of every sample (drq.py:115)
-                self._take_first_aug(st)
+                self._take_first_aug(ST())
                 name = "pi"
             else:
                 name = "obs"
-            self._pack_weights(st)
-            self._encode(name, B, False, st)  # post-critic-step PointNet weights; output detached
+            self._pack_weights(ST())
+            self._encode(name, B, False, ST())  # post-critic-step PointNet weights; output detached
             cat = w[f"cat_{name}"]
             if S:
-                L.copy_cols(self.raw["obs"]["state"], S, 1, 1, cat, ld_cat, D, B, S, st)
-            self._mlp_fwd("actor", cat, D + S, B, w["out_pi"], 2 * A, 2 * A, "actor", st)
+                L.copy_cols(self.raw["obs"]["state"], S, 1, 1, cat, ld_cat, D, B, S, ST())
+            self._mlp_fwd("actor", cat, D + S, B, w["out_pi"], 2 * A, 2 * A, "actor", ST())
             L.tanh_gaussian_fwd(w["out_pi"], B, A, hp.log_std_bound[0], hp.log_std_bound[1], hp.head_scale,
                                 hp.head_bias, noise.get("eps_pi"), self.seed, self.counter, 3, cat[:, D + S:], ld_cat,
-                                w["nlp_pi"], w["eps_pi"], st)
-            self._mlp_fwd("q0", cat, ld_cat, B, w["q_pi"], 2, 1, "q0", st)
-            self._mlp_fwd("q1", cat, ld_cat, B, w["q_pi"][:, 1:], 2, 1, "q1", st)
-            L.actor_loss(w["q_pi"], w["nlp_pi"], B, self.alpha_dev, p["log_alpha"], target_entropy, w["dq"],
-                         w["dlog_alpha"], self.scalars, st)
-            self._mlp_bwd("q0", cat, ld_cat, B, w["dq"], 2, 1, "q0", w["dx0"], False, st)
-            self._mlp_bwd("q1", cat, ld_cat, B, w["dq"][:, 1:], 2, 1, "q1", w["dx1"], False, st)
-            da = w["dx0"][:, D + S:]
-            L.add_cols(da, ld_cat, w["dx1"][:, D + S:], ld_cat, da, ld_cat, B, A, st)
-            L.tanh_gaussian_bwd_dev(w["out_pi"], w["eps_pi"], da, ld_cat, self.alpha_dev, B, A, hp.log_std_bound[0],
-                                    hp.log_std_bound[1], hp.head_scale, w["dout"], st)
+                                w["nlp_pi"], w["eps_pi"], ST())
             a_lo, a_hi = self.layout.group_range["actor"]
             self.grads[a_lo:a_hi].zero_()
-            self._mlp_bwd("actor", cat, D + S, B, w["dout"], 2 * A, 2 * A, "actor", None, True, st)
+            s_q = self._fork(2)
+            with torch.cuda.stream(s_q):
+                self._mlp_fwd("q1", cat, ld_cat, B, w["q_pi"][:, 1:], 2, 1, "q1", ST())
+            self._mlp_fwd("q0", cat, ld_cat, B, w["q_pi"], 2, 1, "q0", ST())
+            self._join(s_q)
+            L.actor_loss(w["q_pi"], w["nlp_pi"], B, self.alpha_dev, p["log_alpha"], target_entropy, w["dq"],
+                         w["dlog_alpha"], self.scalars, ST())
+            s_q = self._fork(2)
+            with torch.cuda.stream(s_q):
+                self._mlp_bwd("q1", cat, ld_cat, B, w["dq"][:, 1:], 2, 1, "q1", w["dx1"], False, ST(), "b")
+            self._mlp_bwd("q0", cat, ld_cat, B, w["dq"], 2, 1, "q0", w["dx0"], False, ST(), "a")
+            self._join(s_q)
+            da = w["dx0"][:, D + S:]
+            L.add_cols(da, ld_cat, w["dx1"][:, D + S:], ld_cat, da, ld_cat, B, A, ST())
+            L.tanh_gaussian_bwd_dev(w["out_pi"], w["eps_pi"], da, ld_cat, self.alpha_dev, B, A, hp.log_std_bound[0],
+                                    hp.log_std_bound[1], hp.head_scale, w["dout"], ST())
+            self._mlp_bwd("actor", cat, D + S, B, w["dout"], 2 * A, 2 * A, "actor", None, True, ST(), "a")
             if self.allreduce is not None:
                 al_lo, al_hi = self.layout.group_range["alpha"]
                 self.allreduce(self.grads[a_lo:al_hi])  # actor grads | d log_alpha in one message
-            self._adam("actor", 1, hp.actor_lr, hp.betas, 8, False, st)
+            self._adam("actor", 1, hp.actor_lr, hp.betas, 8, False, ST())
             if hp.automatic_alpha_tuning:
-                self._adam("alpha", 2, hp.alpha_lr, hp.alpha_betas, None, False, st)
+                self._adam("alpha", 2, hp.alpha_lr, hp.alpha_betas, None, False, ST())
                 self.refresh_alpha()
         self.counter.add_(1)
 

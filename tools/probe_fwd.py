@@ -24,7 +24,7 @@ def run(flags, iters=10):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         L.pointnet_fwd_bf16(eng.w["xh_next"], R, spec.n_points, spec.NP, eng.w["wpack"], c1, c2, c3, spec.ln_eps,
-                            eng.w["pool_keys"], eng.w["pooled_next"], None, st)
+                            eng.w["pool_keys_next"], eng.w["pooled_next"], None, st)
         e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     return float(np.mean(ts[3:]))
@@ -39,7 +39,7 @@ L.cdll.pcrl_debug_set_fwd_flags(ctypes.c_int(0))
 for flags in ():
     L.cdll.pcrl_debug_set_fwd_flags(ctypes.c_int(flags))
     L.pointnet_fwd_bf16(eng.w["xh_next"], R, spec.n_points, spec.NP, eng.w["wpack"], c1, c2, c3, spec.ln_eps,
-                        eng.w["pool_keys"], eng.w["pooled_next"], None, st)
+                        eng.w["pool_keys_next"], eng.w["pooled_next"], None, st)
     torch.cuda.synchronize()
     buf = (ctypes.c_longlong * 4096)()
     n = L.cdll.pcrl_debug_get_trace(buf, 2048)
