@@ -397,20 +397,33 @@ int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, cons
                                                                               c3, w.d2);
   PCRL_CHECK_LAUNCH();
 
-  // 4. layer 2 backward: LN -> dW2, dh1
-  if ((rc = launch_ln_rows_bwd(w.d2, c3, w.y2hat, w.rstd2, g2, dg2, dbe2, w.d2, c3, A, c3, w.total, st))) return rc;
-  if (tf32) {
-    if ((rc = launch_zero_tail(w.d2, c3, w.total, A, st))) return rc;
-    if ((rc = launch_zero_tail(w.h1, c2, w.total, A, st))) return rc;
-    if ((rc = launch_zero_tail(w.h0, c1, w.total, A, st))) return rc;
-    if ((rc = launch_zero_tail(w.xa, CP, w.total, A, st))) return rc;
+  // The weight-gradient GEMMs only feed the optimizer, the data-gradient chain feeds the next layer: run the
+  // wgrads on an internal side stream (event fork/join, graph-capturable) so they overlap the dgrad chain.
+  static cudaStream_t side = nullptr;
+  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  if (!side) {
+    PCRL_CHECK_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    PCRL_CHECK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    PCRL_CHECK_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
   }
-  if ((rc = gemm_tn_acc(w.d2, c3, w.h1, c2, dw2, c2, A, c3, c2, w.total, expect, st, tf32))) return rc;
+  // 4. layer 2 backward: LN -> dW2 (side), dh1 (main)
+  if ((rc = launch_ln_rows_bwd(w.d2, c3, w.y2hat, w.rstd2, g2, dg2, dbe2, w.d2, c3, A, c3, w.total, st))) return rc;
+  PCRL_CHECK_CUDA(cudaEventRecord(ev_fork, st));
+  PCRL_CHECK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+  if (tf32) {  // contraction tails [count, round_up(count, 32)) must be zero for the TMA-fed wgrad GEMMs
+    if ((rc = launch_zero_tail(w.d2, c3, w.total, A, side))) return rc;
+    if ((rc = launch_zero_tail(w.h1, c2, w.total, A, side))) return rc;
+    if ((rc = launch_zero_tail(w.h0, c1, w.total, A, side))) return rc;
+  }
+  if ((rc = gemm_tn_acc(w.d2, c3, w.h1, c2, dw2, c2, A, c3, c2, w.total, expect, side, tf32))) return rc;
   if ((rc = gemm_nn(w.d2, c3, w2, c2, w.d1, c2, A, c3, c2, w.total, st, tf32, w.h1))) return rc;  // ReLU bwd fused
-  // 5. layer 1 backward
+  // 5. layer 1 backward: LN -> dW1 (side), dh0 (main)
   if ((rc = launch_ln_rows_bwd(w.d1, c2, w.y1hat, w.rstd1, g1, dg1, dbe1, w.d1, c2, A, c2, w.total, st))) return rc;
-  if (tf32 && (rc = launch_zero_tail(w.d1, c2, w.total, A, st))) return rc;
-  if ((rc = gemm_tn_acc(w.d1, c2, w.h0, c1, dw1, c1, A, c2, c1, w.total, expect, st, tf32))) return rc;
+  PCRL_CHECK_CUDA(cudaEventRecord(ev_fork, st));
+  PCRL_CHECK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+  if (tf32 && (rc = launch_zero_tail(w.d1, c2, w.total, A, side))) return rc;
+  if ((rc = gemm_tn_acc(w.d1, c2, w.h0, c1, dw1, c1, A, c2, c1, w.total, expect, side, tf32))) return rc;
+  PCRL_CHECK_CUDA(cudaEventRecord(ev_join, side));
   if ((rc = gemm_nn(w.d1, c2, w1, c1, w.d0, c1, A, c2, c1, w.total, st, tf32, w.h0))) return rc;  // ReLU bwd fused
   // 6. layer 0 backward: dW0 [c1,C] += d0^T xa[:, :C];  db0 += colsum(d0)   (exact fp32: raw coordinates)
   {
@@ -419,6 +432,7 @@ int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, cons
     else layer0_wgrad_kernel<16><<<grid, 256, 0, st>>>(w.d0, w.xa, C, c1, w.total, dw0, db0);
     PCRL_CHECK_LAUNCH();
   }
+  PCRL_CHECK_CUDA(cudaStreamWaitEvent(st, ev_join, 0));  // join the wgrad stream
   return PCRL_OK;
 }
 
