@@ -107,6 +107,8 @@ int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, cons
                       const float* g1, const float* be1, const float* w2, const float* g2, const float* be2, int c1,
                       int c2, int c3, float ln_eps, float* dw0, float* db0, float* dw1, float* dg1, float* dbe1,
                       float* dw2, float* dg2, float* dbe2, void* workspace, int64_t workspace_bytes, int tf32,
+                      const void* xh /* optional: bf16 tile images of the same staged points */,
+                      const void* wpack /* optional: packed weights; with xh the recompute runs on the fused tcgen05 kernel */,
                       void* stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -5,6 +5,11 @@
 #include "rowwise.cuh"
 
 namespace pcrl {
+namespace tc {
+int recompute_active_tc(const void* xh, const void* wpack, const int32_t* src, const int* count_dev, int capacity,
+                        int c1, int c2, int c3, float ln_eps, void* xha_scratch, float* h0, float* xhat1, float* rstd1,
+                        float* h1, float* xhat2, float* rstd2, cudaStream_t st);
+}
 
 // max over the N real points of each cloud, ties -> smallest index (torch.max semantics,
 // pointnet.py:151).  h [rows, NP, c3] post-ReLU.  One thread per (cloud, channel): reads are
@@ -354,7 +359,7 @@ int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, cons
                       const float* g1, const float* be1, const float* w2, const float* g2, const float* be2, int c1,
                       int c2, int c3, float ln_eps, float* dw0, float* db0, float* dw1, float* dg1, float* dbe1,
                       float* dw2, float* dg2, float* dbe2, void* workspace, int64_t workspace_bytes, int tf32,
-                      void* stream) {
+                      const void* xh, const void* wpack, void* stream) {
   PCRL_CHECK_ARG(xf && pooled && argmax && dpooled && workspace && dw0 && db0 && dw1 && dg1 && dbe1 && dw2 && dg2 && dbe2);
   PCRL_CHECK_ARG(R >= 0 && NP % 128 == 0 && NP >= N && C <= CP && R <= 1024 * 1024);
   if (R == 0) return PCRL_OK;
@@ -379,6 +384,13 @@ int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, cons
   PCRL_CHECK_LAUNCH();
 
   // 2. recompute the forward of the active points, keeping what LN backward needs
+  if (xh && wpack) {
+    // fast mode: the same fused tcgen05 kernel that produced the argmax, in dump mode (w.d0 doubles as the
+    // gathered bf16 tile scratch: it is only written at the very end of the backward)
+    if ((rc = tc::recompute_active_tc(xh, wpack, w.src, w.total, A, c1, c2, c3, ln_eps, w.d0, w.h0, w.y1hat, w.rstd1,
+                                      w.h1, w.y2hat, w.rstd2, st)))
+      return rc;
+  } else {
   {
     const unsigned grid = (unsigned)cdiv(A, 16);
     if (CP == 8) layer0_fwd_kernel<8><<<grid, 256, 0, st>>>(w.xa, w0, b0, C, c1, w.total, w.h0);
@@ -390,6 +402,7 @@ int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, cons
   if ((rc = gemm_nt(w.h1, c2, w2, c2, nullptr, 0, w.d2, c3, A, c2, c3, w.total, st, tf32))) return rc;
   // (the post-LN activation of layer 2 itself is not needed: only xhat2 / rstd2)
   if ((rc = launch_ln_rows(w.d2, c3, g2, be2, w.d2, c3, w.y2hat, w.rstd2, A, c3, ln_eps, 1, w.total, st))) return rc;
+  }
 
   // 3. dL/dh2: zero except the argmax entries (ReLU mask holds there: pooled > 0)
   PCRL_CHECK_CUDA(cudaMemsetAsync(w.d2, 0, (int64_t)A * c3 * 4, st));

@@ -160,6 +160,13 @@ __device__ __forceinline__ void stats32(const uint32_t (&v)[32], float (&s)[4], 
   }
 }
 
+// "Dump" mode (the sparse backward's recompute): instead of max-pooling, every row's intermediates are written out
+// in fp32 for the LayerNorm / GEMM backward kernels.  rows_dev bounds the compacted rows actually present.
+struct DumpOut {
+  const int* rows_dev;
+  float *h0, *xhat1, *rstd1, *h1, *xhat2, *rstd2;
+};
+
 struct SmemLayout {
   uint32_t w0, w1, w2, prm, xst, act, wkey, stat, bars, total;
 };
@@ -184,7 +191,7 @@ __host__ __device__ inline SmemLayout make_layout(int c1, int c2, int c3) {
 __global__ void __launch_bounds__(kThreads, 1)
 pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpack, int n_tiles, int tiles_per_cloud,
                        int N, int c1, int c2, int c3, float ln_eps, int want_argmax,
-                       unsigned long long* __restrict__ pool_keys) {
+                       unsigned long long* __restrict__ pool_keys, DumpOut dump) {
   extern __shared__ __align__(128) unsigned char smem[];
   const SmemLayout L = make_layout(c1, c2, c3);
   const uint32_t sbase = smem_u32(smem);
@@ -217,7 +224,8 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int n_local = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  if (dump.rows_dev) n_tiles = min(n_tiles, (*dump.rows_dev + 127) >> 7);  // compacted set: size known on the device only
+  const int n_local = max((n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x, 0);
   const uint32_t wbytes = (uint32_t)(c1 * 32 + c2 * c1 * 2 + c3 * c2 * 2 + (2 * c2 + 2 * c3) * 4);
 
   if (warp == 0) {
@@ -353,8 +361,16 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
         const uint32_t sbo = (uint32_t)c1 * 16;
         unsigned char* dst = act + (row >> 3) * sbo + (row & 7) * 16;
         const int col0 = h * (c1 >> 1);
+        float* d_h0 = dump.h0 ? dump.h0 + (tile * 128 + row) * (int64_t)c1 : nullptr;
         for (int ch = col0; ch < col0 + (c1 >> 1); ch += 32) {
           tmem_ld32(tlane + ch, v);
+          if (d_h0) {
+#pragma unroll
+            for (int j4 = 0; j4 < 32; j4 += 4)
+              *reinterpret_cast<float4*>(d_h0 + ch + j4) =
+                  make_float4(fmaxf(__uint_as_float(v[j4]), 0.f), fmaxf(__uint_as_float(v[j4 + 1]), 0.f),
+                              fmaxf(__uint_as_float(v[j4 + 2]), 0.f), fmaxf(__uint_as_float(v[j4 + 3]), 0.f));
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 o;
@@ -383,8 +399,29 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
         uint32_t v[32];
         const uint32_t sbo = (uint32_t)c2 * 16;
         unsigned char* dst = act + (row >> 3) * sbo + (row & 7) * 16;
+        float* d_x1 = dump.xhat1 ? dump.xhat1 + (tile * 128 + row) * (int64_t)c2 : nullptr;
+        float* d_h1 = dump.h1 ? dump.h1 + (tile * 128 + row) * (int64_t)c2 : nullptr;
+        if (d_x1 && h == 0) dump.rstd1[tile * 128 + row] = rstd;
         for (int ch = col0; ch < col0 + (c2 >> 1); ch += 32) {
           tmem_ld32(tlane + ch, v);
+          if (d_x1) {
+#pragma unroll
+            for (int j4 = 0; j4 < 32; j4 += 4) {
+              const float4 gg = *reinterpret_cast<const float4*>(g1 + ch + j4);
+              const float4 bb = *reinterpret_cast<const float4*>(be1 + ch + j4);
+              float4 xh4, hh4;
+              xh4.x = fmaf(__uint_as_float(v[j4]), rstd, nmr);
+              xh4.y = fmaf(__uint_as_float(v[j4 + 1]), rstd, nmr);
+              xh4.z = fmaf(__uint_as_float(v[j4 + 2]), rstd, nmr);
+              xh4.w = fmaf(__uint_as_float(v[j4 + 3]), rstd, nmr);
+              hh4.x = fmaxf(fmaf(xh4.x, gg.x, bb.x), 0.f);
+              hh4.y = fmaxf(fmaf(xh4.y, gg.y, bb.y), 0.f);
+              hh4.z = fmaxf(fmaf(xh4.z, gg.z, bb.z), 0.f);
+              hh4.w = fmaxf(fmaf(xh4.w, gg.w, bb.w), 0.f);
+              *reinterpret_cast<float4*>(d_x1 + ch + j4) = xh4;
+              *reinterpret_cast<float4*>(d_h1 + ch + j4) = hh4;
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float4 ga = *reinterpret_cast<const float4*>(g1 + ch + 8 * j);
@@ -419,6 +456,22 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
         float rstd = 1.f, nmr = 0.f;
         if (!(dbg & 4)) row_stats(col0, c3 >> 1, c3, rstd, nmr);
         if (dbg & 2) row_stats(col0, c3 >> 1, c3, rstd, nmr);
+        if (dump.xhat2) {
+          uint32_t v[32];
+          float* d_x2 = dump.xhat2 + (tile * 128 + row) * (int64_t)c3;
+          if (h == 0) dump.rstd2[tile * 128 + row] = rstd;
+          for (int ch = col0; ch < col0 + (c3 >> 1); ch += 32) {
+            tmem_ld32(tlane + ch, v);
+#pragma unroll
+            for (int j4 = 0; j4 < 32; j4 += 4)
+              *reinterpret_cast<float4*>(d_x2 + ch + j4) =
+                  make_float4(fmaf(__uint_as_float(v[j4]), rstd, nmr), fmaf(__uint_as_float(v[j4 + 1]), rstd, nmr),
+                              fmaf(__uint_as_float(v[j4 + 2]), rstd, nmr), fmaf(__uint_as_float(v[j4 + 3]), rstd, nmr));
+          }
+          tc_fence_before();
+          mbar_arrive(BAR(11 + s));
+          continue;
+        }
         named_bar(1 + s, 256);  // previous tile's combine has finished reading wkey
         // Max over the warp's 32 points per channel without cross-lane reductions: every lane packs
         // (value bits & ~31) | (31 - lane) -- the low 5 mantissa bits carry the lane so ties resolve to the
@@ -499,6 +552,18 @@ __global__ void pool_finalize_kernel(const unsigned long long* __restrict__ keys
   if (argmax) argmax[i] = (int32_t)(0xFFFFFFFFu - (uint32_t)k);
 }
 
+// xha[a] = xh[src[a]] for the compacted rows a < *count: 32 bytes (two 16-byte core-matrix rows) per point
+__global__ void gather_xh_kernel(const char* __restrict__ xh, const int32_t* __restrict__ src, const int* __restrict__ count,
+                                 char* __restrict__ xha) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= *count) return;
+  const int pidx = src[a];
+  const char* sp_ = xh + (int64_t)(pidx >> 7) * kTileBytes + ((pidx & 127) >> 3) * 256 + (pidx & 7) * 16;
+  char* dp = xha + (int64_t)(a >> 7) * kTileBytes + ((a & 127) >> 3) * 256 + (a & 7) * 16;
+  *reinterpret_cast<uint4*>(dp) = *reinterpret_cast<const uint4*>(sp_);
+  *reinterpret_cast<uint4*>(dp + 128) = *reinterpret_cast<const uint4*>(sp_ + 128);
+}
+
 // byte offset of element (row n, k) in a K-major no-swizzle image with K columns
 __device__ __forceinline__ uint32_t img_off(int n, int k, int K) {
   return (uint32_t)((n >> 3) * (K * 16) + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2);
@@ -545,6 +610,28 @@ static bool shapes_ok(int c1, int c2, int c3) {
   // every layer's channels split into two halves of whole 32-column chunks; the activation buffer doubles as
   // the 32 KB max-pool transpose scratch (8 warps x 4 KB): needs max(c1, c2) >= 128
   return ok(c1, 64) && ok(c2, 64) && ok(c3, 64) && (c1 >= 128 || c2 >= 128) && make_layout(c1, c2, c3).total <= 227 * 1024;
+}
+
+// Recompute of the compacted active points on the fused tensor-core kernel (called by pcrl_pointnet_bwd in fast mode):
+// gathers their bf16 tile rows, runs the three layers and writes h0 / xhat1 / rstd1 / h1 / xhat2 / rstd2 (fp32).
+int recompute_active_tc(const void* xh, const void* wpack, const int32_t* src, const int* count_dev, int capacity,
+                        int c1, int c2, int c3, float ln_eps, void* xha_scratch, float* h0, float* xhat1, float* rstd1,
+                        float* h1, float* xhat2, float* rstd2, cudaStream_t st) {
+  if (!shapes_ok(c1, c2, c3)) {
+    set_error("recompute_active_tc: widths unsupported by the tcgen05 path");
+    return PCRL_EUNSUPPORTED;
+  }
+  gather_xh_kernel<<<(unsigned)cdiv(capacity, 256), 256, 0, st>>>((const char*)xh, src, count_dev, (char*)xha_scratch);
+  PCRL_CHECK_LAUNCH();
+  const SmemLayout L = make_layout(c1, c2, c3);
+  PCRL_CHECK_CUDA(cudaFuncSetAttribute(pointnet_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  const int n_tiles = (int)cdiv(capacity, 128);
+  DumpOut d{count_dev, h0, xhat1, rstd1, h1, xhat2, rstd2};
+  pointnet_fwd_tc_kernel<<<std::min(sm_count(), n_tiles), kThreads, L.total, st>>>(
+      (const char*)xha_scratch, (const char*)wpack, n_tiles, /*tiles_per_cloud=*/1 << 30, /*N=*/0, c1, c2, c3, ln_eps, 0,
+      nullptr, d);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
 }
 
 }  // namespace tc
@@ -612,7 +699,7 @@ int pcrl_pointnet_fwd_bf16(const void* xh, int R, int N, int NP, const void* wpa
   tc::pointnet_fwd_tc_kernel<<<grid, tc::kThreads, L.total, st>>>((const char*)xh, (const char*)wpack, n_tiles,
                                                                   tiles_per_cloud, N, c1, c2, c3, ln_eps,
                                                                   argmax != nullptr,
-                                                                  (unsigned long long*)pool_keys);
+                                                                  (unsigned long long*)pool_keys, tc::DumpOut{});
   PCRL_CHECK_LAUNCH();
   const int64_t n = (int64_t)R * c3;
   tc::pool_finalize_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>((const unsigned long long*)pool_keys, n, pooled,

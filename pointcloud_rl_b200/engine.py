@@ -466,7 +466,8 @@ class UpdateEngine:
         L.pointnet_bwd(w["xf_obs"], R, sp.n_points, sp.NP, sp.CP, sp.C, w["pooled_obs"], w["argmax_obs"], w["dpooled"],
                        p["pn.w0"], p["pn.b0"], p["pn.w1"], p["pn.g1"], p["pn.be1"], p["pn.w2"], p["pn.g2"],
                        p["pn.be2"], c1, c2, c3, sp.ln_eps, g["pn.w0"], g["pn.b0"], g["pn.w1"], g["pn.g1"], g["pn.be1"],
-                       g["pn.w2"], g["pn.g2"], g["pn.be2"], w["scratch"], self.bwd_ws_bytes, self.tf32, ST())
+                       g["pn.w2"], g["pn.g2"], g["pn.be2"], w["scratch"], self.bwd_ws_bytes, self.tf32, w.get("xh_obs"),
+                       w.get("wpack"), ST())
         if self.allreduce is not None:
             self.allreduce(self.grads[c_lo:c_lo + self.layout.q_range[0]])  # PointNet gradients (0.3 MB)
             q_pending.wait()

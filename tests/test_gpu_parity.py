@@ -282,7 +282,7 @@ def test_pointnet_bwd_sparse_matches_autograd(L, tf32):
     ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
     L.pointnet_bwd(xf, R, N, NP, CP, C, pooled, argmax, dpool.cuda(), d["pn.w0"], d["pn.b0"], d["pn.w1"], d["pn.g1"],
                    d["pn.be1"], d["pn.w2"], d["pn.g2"], d["pn.be2"], c1, c2, c3, 1e-6, *[grads[k] for k in keys], ws,
-                   nbytes, tf32, sp())
+                   nbytes, tf32, None, None, sp())
     errs = {k: rel_err(grads[k], leaves[k].grad) for k in keys}
     # tf32=1 is the fast ("bf16") mode: tensor-core GEMMs with 10-bit-mantissa operands, and LayerNorm's backward
     # amplifies their rounding through its two projections -> judged at the bf16 tolerance (2e-2)
