@@ -438,8 +438,14 @@ int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, cons
   if ((rc = gemm_tn_acc(w.d1, c2, w.h0, c1, dw1, c1, A, c2, c1, w.total, expect, side, tf32))) return rc;
   PCRL_CHECK_CUDA(cudaEventRecord(ev_join, side));
   if ((rc = gemm_nn(w.d1, c2, w1, c1, w.d0, c1, A, c2, c1, w.total, st, tf32, w.h0))) return rc;  // ReLU bwd fused
-  // 6. layer 0 backward: dW0 [c1,C] += d0^T xa[:, :C];  db0 += colsum(d0)   (exact fp32: raw coordinates)
-  {
+  // 6. layer 0 backward: dW0 [c1,C] += d0^T xa[:, :C];  db0 += colsum(d0)
+  if (tf32) {
+    // fast mode: one more split-K tensor-core GEMM (N = C padded to a 32-column tile) + a column sum
+    if ((rc = launch_zero_tail(w.d0, c1, w.total, A, st))) return rc;
+    if ((rc = launch_zero_tail(w.xa, CP, w.total, A, st))) return rc;
+    if ((rc = gemm_tn_acc(w.d0, c1, w.xa, CP, dw0, C, A, c1, C, w.total, expect, st, 1))) return rc;
+    if ((rc = launch_colsum(w.d0, c1, A, c1, w.total, db0, st))) return rc;
+  } else {  // parity mode: exact fp32 on the raw coordinates
     const unsigned grid = (unsigned)cdiv(A, 256);
     if (CP == 8) layer0_wgrad_kernel<8><<<grid, 256, 0, st>>>(w.d0, w.xa, C, c1, w.total, dw0, db0);
     else layer0_wgrad_kernel<16><<<grid, 256, 0, st>>>(w.d0, w.xa, C, c1, w.total, dw0, db0);
