@@ -15,7 +15,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
-]
+] + os.environ.get("PCRL_NVCC_EXTRA", "").split()  # e.g. -DPCRL_FWD_TRACE for tools/probe_fwd.py
 
 
 def _sources():

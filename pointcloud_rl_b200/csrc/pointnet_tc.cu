@@ -43,9 +43,9 @@ struct Tracer {  // register-resident cursor, plain stores: no atomics or round 
   }
 };
 
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kTileBytes = 128 * 16 * 2;  // one X tile: 128 points x 16 bf16
-constexpr int kThreads = 64 + 2 * 8 * 32;  // TMA warp + MMA warp + 2 slots x 8 epilogue warps
+constexpr int kThreads = 128 + 256 + 256;  // warp 0 TMA, 1 MMA issuer (layers 0/1), 2 MMA issuer (layer 2), 3 idle; 8 warps layers 0/1; 8 warps layer 2
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -68,6 +68,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE_%=:\n\t}" ::"r"(bar),
       "r"(parity)
       : "memory");
+}
+// wait with back-off: for warps that are ahead of the pipeline's bottleneck stage.  A spinning try_wait is an MIO
+// (shared-memory pipe) transaction plus issue slots every few cycles, taken from the warps that are doing the work.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, unsigned ns) {
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    __nanosleep(ns);
+  }
 }
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -167,8 +183,35 @@ struct DumpOut {
   float *h0, *xhat1, *rstd1, *h1, *xhat2, *rstd2;
 };
 
+// Packed weight buffer (pcrl_pointnet_pack_weights):
+//   [ W0' | W1 | W2s | g1 be1 g2 be2 (fp32) ]   <- loaded into shared memory as one image by the max-pool forward
+//   [ pos[c3] (int32) | n_pos (int32, padded to 16 B) ]
+//   [ W2 ]                                       <- plain layer-2 image, used by the dump (backward recompute) mode
+// W2s is W2 with its rows permuted and sign-flipped: row pos[c] = sign(g2[c]) * W2[c, :], channels with g2 >= 0 first
+// (n_pos of them).  max_p(g*x + b) = |g| * max_p(sign(g)*x) + b, so the layer-2 epilogue max-pools z = sign(g2)*xhat
+// directly -- no gamma/beta loads and one FFMA less per element in the hot loop -- and the affine part runs once per
+// (cloud, channel) in pool_finalize_kernel.
+struct WpackLayout {
+  uint32_t w0, w1, w2s, prm, pos, npos, w2, total, img_bytes;
+};
+__host__ __device__ inline WpackLayout make_wpack(int c1, int c2, int c3) {
+  WpackLayout W;
+  uint32_t o = 0;
+  W.w0 = o;   o += c1 * 32;
+  W.w1 = o;   o += c2 * c1 * 2;
+  W.w2s = o;  o += c3 * c2 * 2;
+  W.prm = o;  o += (2 * c2 + 2 * c3) * 4;
+  W.img_bytes = o;
+  W.pos = o;  o += c3 * 4;
+  W.npos = o; o += 16;
+  W.w2 = o;   o += c3 * c2 * 2;
+  W.total = o;
+  return W;
+}
+constexpr float kKeyBias = 16.0f;  // |xhat| <= sqrt(C) <= 16 for C <= 256: z + 16 > 0, so float order == integer order
+
 struct SmemLayout {
-  uint32_t w0, w1, w2, prm, xst, act, wkey, stat, bars, total;
+  uint32_t w0, w1, w2, prm, xst, act0, act1, tr, wkey, stat, bars, total;
 };
 __host__ __device__ inline SmemLayout make_layout(int c1, int c2, int c3) {
   SmemLayout L;
@@ -179,15 +222,24 @@ __host__ __device__ inline SmemLayout make_layout(int c1, int c2, int c3) {
   L.prm = o;  o += (2 * c2 + 2 * c3) * 4;
   o = (o + 127) & ~127u;
   L.xst = o;  o += kStages * kTileBytes;
-  const int kmax = c1 > c2 ? c1 : c2;
-  L.act = o;  o += 2 * 128 * kmax * 2;
-  L.wkey = o; o += 2 * 4 * c3 * 8;
-  L.stat = o; o += 2 * 2 * 128 * 8;  // per slot, per channel half: (sum, sumsq) of every row
-  L.bars = o; o += 128;
+  L.act0 = o; o += 128 * c1 * 2;  // h0 (bf16 UMMA image): layer-0 epilogue -> layer-1 MMA
+  L.act1 = o; o += 128 * c2 * 2;  // h1: layer-1 epilogue -> layer-2 MMA
+  L.tr = o;   o += 8 * 4096;      // max-pool transpose scratch: 4 KB per layer-2 warp
+  L.wkey = o; o += 4 * c3 * 8;
+  L.stat = o; o += 2 * 2 * 128 * 8;  // per group, per channel half: (sum, sumsq) of every row
+  L.bars = o; o += 256;
   L.total = o;
   return L;
 }
 
+// The layers run as a pipeline over consecutive 128-point tiles.
+//   * warps 4..11 ("front" group) do the layer-0 and layer-1 epilogues of tile i+1 while
+//   * warps 12..19 ("pool" group) normalise and max-pool layer 2 of tile i, and the tensor pipe runs under both.
+// TMEM (512 columns): [0, max(c1,c2)) is the accumulator of layers 0 and 1 (they alias: the front group is a serial
+// chain anyway), followed by a ring of three half-accumulators of c3/2 columns for layer 2.  Layer 2 is issued as
+// two N = c3/2 MMAs per tile; tile i uses ring slots (2i)%3 and (2i+1)%3, so the first half of tile i+1 can be
+// computed while the pool group still reads tile i, and the second half as soon as the pool group has drained the
+// first half of tile i: the pool group, which is the bottleneck stage, never waits for the tensor pipe.
 __global__ void __launch_bounds__(kThreads, 1)
 pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpack, int n_tiles, int tiles_per_cloud,
                        int N, int c1, int c2, int c3, float ln_eps, int want_argmax,
@@ -197,20 +249,36 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // barriers: [0] weights, [1..4] xfull, [5..8] xempty, [9,10] accfull, [11,12] actready; then tmem ptr
+  // mbarriers
+  constexpr int WB = 0;              // weights landed
+  constexpr int XF = 1;              // [kStages] x tile landed
+  constexpr int XE = XF + kStages;   // [kStages] x stage free
+  constexpr int F0 = XE + kStages;   // layer-0 accumulator complete (tcgen05.commit)
+  constexpr int F1 = F0 + 1;         // layer-1 accumulator complete
+  constexpr int F2 = F1 + 1;         // both layer-2 halves complete (2 commits)
+  constexpr int E0 = F2 + 1;         // front group: h0 written, accumulator drained (256 arrivals)
+  constexpr int E1 = E0 + 1;         // front group: h1 written, accumulator drained
+  constexpr int DA = E1 + 1;         // [2, by tile parity] pool group drained the first layer-2 half
+  constexpr int DB = DA + 2;         // [2, by tile parity] ... the second half
+  constexpr int NBAR = DB + 2;
   const uint32_t bar0 = sbase + L.bars;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L.bars + 13 * 8);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L.bars + NBAR * 8);
 
   if (threadIdx.x == 0) {
-    mbar_init(BAR(0), 1);
+    mbar_init(BAR(WB), 1);
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(BAR(1 + s), 1);
-      mbar_init(BAR(5 + s), 1);
+      mbar_init(BAR(XF + s), 1);
+      mbar_init(BAR(XE + s), 1);
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(BAR(9 + s), 1);
-      mbar_init(BAR(11 + s), 256);
+    mbar_init(BAR(F0), 1);
+    mbar_init(BAR(F1), 1);
+    mbar_init(BAR(F2), 2);
+    mbar_init(BAR(E0), 256);
+    mbar_init(BAR(E1), 256);
+    for (int k = 0; k < 2; ++k) {
+      mbar_init(BAR(DA + k), 256);
+      mbar_init(BAR(DB + k), 256);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -227,139 +295,118 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
   if (dump.rows_dev) n_tiles = min(n_tiles, (*dump.rows_dev + 127) >> 7);  // compacted set: size known on the device only
   const int n_local = max((n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x, 0);
   const uint32_t wbytes = (uint32_t)(c1 * 32 + c2 * c1 * 2 + c3 * c2 * 2 + (2 * c2 + 2 * c3) * 4);
+  const int dbg = g_dbg;
+  const int ch2 = c3 >> 1;                                   // channels per layer-2 half
+  const uint32_t ring0 = tmem_base + (uint32_t)(c1 > c2 ? c1 : c2);  // first ring slot
+  // ring slot (TMEM column base) of layer-2 half `half` of local tile i
+  auto ring = [&](int i, int half) { return ring0 + (uint32_t)(((2 * i + half) % 3) * ch2); };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_expect_tx(BAR(0), wbytes);
-      // weights + LN parameters are one contiguous image laid out exactly like the smem carve-up
+      mbar_expect_tx(BAR(WB), wbytes);
+      // weights + LN parameters are one contiguous image laid out exactly like the smem carve-up; the dump mode
+      // swaps in the plain (unpermuted, unsigned) layer-2 weights
+      const WpackLayout W = make_wpack(c1, c2, c3);
       uint32_t off = 0;
       while (off < wbytes) {
         uint32_t n = min(wbytes - off, 32768u);
-        bulk_g2s(sbase + L.w0 + off, wpack + off, n, BAR(0));
+        uint32_t src = off;
+        if (dump.xhat2 && off >= W.w2s && off < W.prm) {
+          n = min(n, W.prm - off);
+          src = W.w2 + (off - W.w2s);
+        } else if (dump.xhat2 && off < W.w2s) {
+          n = min(n, W.w2s - off);
+        }
+        bulk_g2s(sbase + L.w0 + off, wpack + src, n, BAR(WB));
         off += n;
       }
       for (int i = 0; i < n_local; ++i) {
         const int st = i % kStages;
-        if (i >= kStages) mbar_wait(BAR(5 + st), ((i / kStages) - 1) & 1);
-        mbar_expect_tx(BAR(1 + st), kTileBytes);
+        if (i >= kStages) mbar_wait_relaxed(BAR(XE + st), ((i / kStages) - 1) & 1, 100);
+        mbar_expect_tx(BAR(XF + st), kTileBytes);
         const int64_t tile = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
-        bulk_g2s(sbase + L.xst + st * kTileBytes, xh + tile * kTileBytes, kTileBytes, BAR(1 + st));
+        bulk_g2s(sbase + L.xst + st * kTileBytes, xh + tile * kTileBytes, kTileBytes, BAR(XF + st));
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+    // ------------------------------------------------------------------ MMA issuer, layers 0 and 1 (a serial chain per tile)
     if (lane == 0) {
-      mbar_wait(BAR(0), 0);
-      const uint32_t id0 = make_idesc(c1), id1 = make_idesc(c2), id2 = make_idesc(c3);
-      const int kmax = c1 > c2 ? c1 : c2;
-      // per-slot progress: tile index (s, s+2, ...), layer, and how many epilogue hand-offs were consumed.
-      // The issuer polls both slots and launches whichever is ready, so a slow epilogue on one slot never
-      // holds back the other slot's next layer.
-      Tracer trace{0, 0, (g_dbg & 128) && blockIdx.x == 0};
-      int tile_i[2] = {0, 1}, layer[2] = {0, 0};
-      uint32_t ph_act[2] = {0, 0};
-      bool first[2] = {true, true};
-      while (tile_i[0] < n_local || tile_i[1] < n_local) {
-        bool progressed = false;
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const int i = tile_i[s];
-          if (i >= n_local) continue;
-          const uint32_t d_tmem = tmem_base + (uint32_t)(s * 256);
-          const uint32_t act = sbase + L.act + (uint32_t)(s * 128 * kmax * 2);
-          if (layer[s] == 0) {
-            const int st = i % kStages;
-            if (!mbar_test(BAR(1 + st), (i / kStages) & 1)) continue;                  // point tile landed?
-            if (!first[s] && !mbar_test(BAR(11 + s), ph_act[s] & 1)) continue;         // previous layer-2 accumulator drained?
-            if (!first[s]) ph_act[s]++;
-            first[s] = false;
-            trace(100 + s * 10 + 0);
-            tc_fence_after();
-            mma_bf16(d_tmem, make_desc(sbase + L.xst + st * kTileBytes, 256), make_desc(sbase + L.w0, 256), id0, 0);
-            mma_commit(BAR(5 + st));
-          } else {
-            if (!mbar_test(BAR(11 + s), ph_act[s] & 1)) continue;                      // h_{layer-1} written?
-            ph_act[s]++;
-            trace(100 + s * 10 + layer[s]);
-            tc_fence_after();
-            const int K = (layer[s] == 1) ? c1 : c2;
-            const uint32_t wb = sbase + ((layer[s] == 1) ? L.w1 : L.w2);
-            const uint32_t idesc = (layer[s] == 1) ? id1 : id2;
-            for (int ks = 0; ks < K / 16; ++ks)
-              mma_bf16(d_tmem, make_desc(act + ks * 256, K * 16), make_desc(wb + ks * 256, K * 16), idesc, ks > 0);
-          }
-          mma_commit(BAR(9 + s));
-          trace(200 + s * 10 + layer[s]);
-          progressed = true;
-          if (++layer[s] == 3) {
-            layer[s] = 0;
-            tile_i[s] += 2;
-          }
-        }
-        if (!progressed && !(g_dbg & 16)) __nanosleep(40);
+      mbar_wait(BAR(WB), 0);
+      const uint32_t id0 = make_idesc(c1), id1 = make_idesc(c2);
+      Tracer trace{0, 0, (dbg & 128) && blockIdx.x == 0};
+      for (int j = 0; j < n_local; ++j) {
+        const int st = j % kStages;
+        mbar_wait(BAR(XF + st), (j / kStages) & 1);
+        if (j > 0) mbar_wait(BAR(E1), (j - 1) & 1);  // layer-1 epilogue of the previous tile drained the shared accumulator
+        trace(100);
+        tc_fence_after();
+        mma_bf16(tmem_base, make_desc(sbase + L.xst + st * kTileBytes, 256), make_desc(sbase + L.w0, 256), id0, 0);
+        mma_commit(BAR(XE + st));
+        mma_commit(BAR(F0));
+        trace(200);
+        mbar_wait(BAR(E0), j & 1);  // h0 in shared memory, accumulator drained
+        trace(101);
+        tc_fence_after();
+        for (int ks = 0; ks < c1 / 16; ++ks)
+          mma_bf16(tmem_base, make_desc(sbase + L.act0 + ks * 256, c1 * 16), make_desc(sbase + L.w1 + ks * 256, c1 * 16), id1, ks > 0);
+        mma_commit(BAR(F1));
+        trace(201);
       }
     }
-  } else {
-    // ------------------------------------------------------------------ epilogue warps
-    // 8 warps per slot: two warps share each TMEM lane quadrant (hardware rule: a warp reaches lanes
-    // 32*(warp%4)..+31) and split the channels in halves.  LayerNorm needs whole-row statistics, so the pair
-    // exchanges its partial (sum, sum of squares) through shared memory around a 64-thread named barrier.
-    // Four epilogue warps per SM sub-partition instead of two: the epilogue is instruction-issue bound.
-    const int ew = warp - 2;
-    const int s = ew >> 3;               // slot
-    const int h = (ew >> 2) & 1;         // which half of the channels this warp owns
-    const int q = warp & 3;              // TMEM lane quadrant
-    const int row = q * 32 + lane;       // point within the tile
-    const int kmax = c1 > c2 ? c1 : c2;
-    unsigned char* act = smem + L.act + s * 128 * kmax * 2;
-    const float* prm = reinterpret_cast<const float*>(smem + L.prm);
-    const float *g1 = prm, *be1 = prm + c2, *g2 = prm + 2 * c2, *be2 = prm + 2 * c2 + c3;
-    unsigned long long* wkey = reinterpret_cast<unsigned long long*>(smem + L.wkey) + (s * 4 + q) * c3;
-    const unsigned long long* wkey_slot = reinterpret_cast<unsigned long long*>(smem + L.wkey) + s * 4 * c3;
-    float2* stat_mine = reinterpret_cast<float2*>(smem + L.stat) + (s * 2 + h) * 128 + row;
-    const float2* stat_peer = reinterpret_cast<const float2*>(smem + L.stat) + (s * 2 + (h ^ 1)) * 128 + row;
-    const int pair_bar = 3 + s * 4 + q;
-    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 256);
-    const int tid_slot = threadIdx.x - (64 + s * 256);
-    uint32_t ph_acc = 0;
-    mbar_wait(BAR(0), 0);  // LN parameters landed
-    const int dbg = g_dbg;
-    Tracer trace_e{1 + s, 0, (dbg & 128) && blockIdx.x == 0 && (ew & 7) == 0 && lane == 0};
-
-    // whole-row LayerNorm statistics from this warp's half [col0, col0 + ncols) plus the partner's partial
-    auto row_stats = [&](int col0, int ncols, int width, float& rstd, float& nmr) {
-      uint32_t v[32];
-      float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int ch = 0; ch < ncols; ch += 32) {
-        tmem_ld32(tlane + col0 + ch, v);
-        stats32(v, s4, q4);
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ MMA issuer, layer 2 (two N = c3/2 halves into the ring)
+    if (lane == 0) {
+      mbar_wait(BAR(WB), 0);
+      const uint32_t id2 = make_idesc(ch2);
+      const uint32_t w2b = sbase + L.w2 + (uint32_t)(ch2 >> 3) * (uint32_t)(c2 * 16);  // rows ch2.. of the W2 image
+      Tracer trace{1, 0, (dbg & 128) && blockIdx.x == 0};
+      for (int j = 0; j < n_local; ++j) {
+        mbar_wait(BAR(E1), j & 1);  // h1 of tile j in shared memory
+        // first half -> ring slot last used by the second half of tile j-2
+        if (j >= 2) mbar_wait(BAR(DB + (j & 1)), ((j - 2) >> 1) & 1);
+        trace(102);
+        tc_fence_after();
+        for (int ks = 0; ks < c2 / 16; ++ks)
+          mma_bf16(ring(j, 0), make_desc(sbase + L.act1 + ks * 256, c2 * 16), make_desc(sbase + L.w2 + ks * 256, c2 * 16), id2, ks > 0);
+        mma_commit(BAR(F2));
+        trace(202);
+        // second half -> ring slot last used by the first half of tile j-1
+        if (j >= 1) mbar_wait(BAR(DA + ((j - 1) & 1)), ((j - 1) >> 1) & 1);
+        trace(103);
+        tc_fence_after();
+        for (int ks = 0; ks < c2 / 16; ++ks)
+          mma_bf16(ring(j, 1), make_desc(sbase + L.act1 + ks * 256, c2 * 16), make_desc(w2b + ks * 256, c2 * 16), id2, ks > 0);
+        mma_commit(BAR(F2));
+        trace(203);
       }
-      float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]), sq = (q4[0] + q4[1]) + (q4[2] + q4[3]);
-      *stat_mine = make_float2(sum, sq);
-      named_bar(pair_bar, 64);
-      const float2 o = *stat_peer;
-      sum += o.x;
-      sq += o.y;
-      const float mean = sum / (float)width;
-      const float var = fmaxf(sq / (float)width - mean * mean, 0.f);
-      rstd = rsqrtf(var + ln_eps);
-      nmr = -mean * rstd;
-    };
-
-    for (int i = s; i < n_local; i += 2) {
+    }
+  } else if (warp == 3) {
+    // idle: the register file is allocated in units of four warps anyway
+  } else if (warp < 12) {
+    // ------------------------------------------------------------------ front group: layer-0 and layer-1 epilogues
+    // 8 warps: two per TMEM lane quadrant (hardware rule: a warp reaches lanes 32*(warp%4)..+31), each taking half
+    // of the channels.  LayerNorm needs whole-row statistics, so the pair swaps its partial (sum, sum of squares)
+    // through shared memory around a 64-thread named barrier.
+    const int h = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float* prm = reinterpret_cast<const float*>(smem + L.prm);
+    const float *g1 = prm, *be1 = prm + c2;
+    unsigned char* dst0 = smem + L.act0 + (row >> 3) * (uint32_t)(c1 * 16) + (row & 7) * 16;
+    unsigned char* dst1 = smem + L.act1 + (row >> 3) * (uint32_t)(c2 * 16) + (row & 7) * 16;
+    float2* stat_mine = reinterpret_cast<float2*>(smem + L.stat) + (2 + h) * 128 + row;
+    const float2* stat_peer = reinterpret_cast<const float2*>(smem + L.stat) + (2 + (h ^ 1)) * 128 + row;
+    const int pair_bar = 6 + q;
+    mbar_wait(BAR(WB), 0);  // LN parameters landed
+    for (int i = 0; i < n_local; ++i) {
       const int64_t tile = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
-      const int cloud = (int)(tile / tiles_per_cloud);
-
-      // ---- layer 0: relu -> bf16 -> activation buffer (K = c1)
-      mbar_wait(BAR(9 + s), ph_acc & 1);
-      ph_acc++;
-      trace_e(300 + s * 10 + 0);
+      uint32_t v[32];
+      // ---- layer 0: ReLU -> bf16 operand of layer 1
+      mbar_wait(BAR(F0), i & 1);
       tc_fence_after();
       if (!(dbg & 64)) {
-        uint32_t v[32];
-        const uint32_t sbo = (uint32_t)c1 * 16;
-        unsigned char* dst = act + (row >> 3) * sbo + (row & 7) * 16;
         const int col0 = h * (c1 >> 1);
         float* d_h0 = dump.h0 ? dump.h0 + (tile * 128 + row) * (int64_t)c1 : nullptr;
         for (int ch = col0; ch < col0 + (c1 >> 1); ch += 32) {
@@ -378,27 +425,37 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
             o.y = pack_relu_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
             o.z = pack_relu_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
             o.w = pack_relu_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-            *reinterpret_cast<uint4*>(dst + ((ch >> 3) + j) * 128) = o;
+            *reinterpret_cast<uint4*>(dst0 + ((ch >> 3) + j) * 128) = o;
           }
         }
       }
       fence_async_smem();
       tc_fence_before();
-      mbar_arrive(BAR(11 + s));
-      trace_e(400 + s * 10 + 0);
+      mbar_arrive(BAR(E0));
 
-      // ---- layer 1: LN over channels + relu -> bf16 -> activation buffer (K = c2)
-      mbar_wait(BAR(9 + s), ph_acc & 1);
-      ph_acc++;
-      trace_e(300 + s * 10 + 1);
+      // ---- layer 1: LN over channels + ReLU -> bf16 operand of layer 2
+      mbar_wait(BAR(F1), i & 1);
       tc_fence_after();
+      float rstd = 1.f, nmr = 0.f;
+      const int col0 = h * (c2 >> 1);
       if (!(dbg & 32)) {
-        const int col0 = h * (c2 >> 1);
-        float rstd, nmr;
-        row_stats(col0, c2 >> 1, c2, rstd, nmr);
-        uint32_t v[32];
-        const uint32_t sbo = (uint32_t)c2 * 16;
-        unsigned char* dst = act + (row >> 3) * sbo + (row & 7) * 16;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int ch = 0; ch < (c2 >> 1); ch += 32) {
+          tmem_ld32(tlane + col0 + ch, v);
+          stats32(v, s4, q4);
+        }
+        float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]), sq = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+        *stat_mine = make_float2(sum, sq);
+        named_bar(pair_bar, 64);
+        const float2 o = *stat_peer;
+        sum += o.x;
+        sq += o.y;
+        const float mean = sum / (float)c2;
+        rstd = rsqrtf(fmaxf(sq / (float)c2 - mean * mean, 0.f) + ln_eps);
+        nmr = -mean * rstd;
+      }
+      if (i > 0) mbar_wait(BAR(F2), (i - 1) & 1);  // both layer-2 MMAs of the previous tile have finished reading h1
+      if (!(dbg & 32)) {
         float* d_x1 = dump.xhat1 ? dump.xhat1 + (tile * 128 + row) * (int64_t)c2 : nullptr;
         float* d_h1 = dump.h1 ? dump.h1 + (tile * 128 + row) * (int64_t)c2 : nullptr;
         if (d_x1 && h == 0) dump.rstd1[tile * 128 + row] = rstd;
@@ -438,99 +495,168 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
             pk.y = pack_relu_bf16x2(o[2], o[3]);
             pk.z = pack_relu_bf16x2(o[4], o[5]);
             pk.w = pack_relu_bf16x2(o[6], o[7]);
-            *reinterpret_cast<uint4*>(dst + ((ch >> 3) + j) * 128) = pk;
+            *reinterpret_cast<uint4*>(dst1 + ((ch >> 3) + j) * 128) = pk;
           }
         }
       }
       fence_async_smem();
       tc_fence_before();
-      mbar_arrive(BAR(11 + s));
-      trace_e(400 + s * 10 + 1);
+      mbar_arrive(BAR(E1));
+    }
+  } else {
+    // ------------------------------------------------------------------ pool group: layer-2 LN, then max (and argmax) over the tile's points
+    // 8 warps, two per TMEM lane quadrant; warp (q, h) owns channel quarter h of BOTH layer-2 halves, so the first
+    // half's ring slot is released after half of the work.
+    const int h = (warp - 12) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;  // point within the tile
+    const int cq = ch2 >> 1;        // channels per (half, warp)
+    unsigned long long* wkey = reinterpret_cast<unsigned long long*>(smem + L.wkey) + q * c3;
+    const unsigned long long* wkey_all = reinterpret_cast<unsigned long long*>(smem + L.wkey);
+    float2* stat_mine = reinterpret_cast<float2*>(smem + L.stat) + h * 128 + row;
+    const float2* stat_peer = reinterpret_cast<const float2*>(smem + L.stat) + (h ^ 1) * 128 + row;
+    const int pair_bar = 2 + q;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const int tid_grp = threadIdx.x - (128 + 256);
+    // dump mode runs on the plain layer-2 weights: every channel counts as positive
+    const int n_pos = dump.xhat2 ? c3 : *reinterpret_cast<const int*>(wpack + make_wpack(c1, c2, c3).npos);
+    mbar_wait(BAR(WB), 0);  // LN parameters landed
+    Tracer trace_e{2, 0, (dbg & 128) && blockIdx.x == 0 && warp == 12 && lane == 0};
 
-      // ---- layer 2: LN, then max (and argmax) over the tile's points; ReLU is applied after the max
-      mbar_wait(BAR(9 + s), ph_acc & 1);
-      ph_acc++;
+    uint32_t* tr = reinterpret_cast<uint32_t*>(smem + L.tr) + (warp - 12) * 1024;  // 4 KB per warp
+    const uint32_t lane_tag = 31u - (uint32_t)lane;
+    uint32_t st_off[8], ld_off[8];  // XOR-swizzled word offsets of the transpose tile
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      st_off[k] = (uint32_t)(lane * 32 + ((k ^ (lane & 7)) << 2));
+      ld_off[k] = (uint32_t)((((lane >> 2) ^ k) << 2) + (lane & 3));
+    }
+
+    for (int i = 0; i < n_local; ++i) {
+      const int64_t tile = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
+      const int cloud = (int)(tile / tiles_per_cloud);
+      const uint32_t idx_base = (uint32_t)((int)(tile % tiles_per_cloud) * 128 + q * 32);
+      mbar_wait(BAR(F2), i & 1);
+      trace_e(300);
       tc_fence_after();
-      {
-        const int col0 = h * (c3 >> 1);
-        float rstd = 1.f, nmr = 0.f;
-        if (!(dbg & 4)) row_stats(col0, c3 >> 1, c3, rstd, nmr);
-        if (dbg & 2) row_stats(col0, c3 >> 1, c3, rstd, nmr);
-        if (dump.xhat2) {
-          uint32_t v[32];
-          float* d_x2 = dump.xhat2 + (tile * 128 + row) * (int64_t)c3;
-          if (h == 0) dump.rstd2[tile * 128 + row] = rstd;
-          for (int ch = col0; ch < col0 + (c3 >> 1); ch += 32) {
-            tmem_ld32(tlane + ch, v);
+      uint32_t v[32];
+      float rstd = 1.f, nmr = 0.f;
+      if (!(dbg & 4)) {
+        // the accumulator holds y' = sign(g2) * y (channels with g2 >= 0 first): sum of squares is unchanged, the
+        // mean needs the signs back
+        float sum = 0.f, q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t t0 = ring(i, half) + lane_off + (uint32_t)(h * cq);
+          const int cbase = half * ch2 + h * cq;
+          for (int ch = 0; ch < cq; ch += 32) {
+            tmem_ld32(t0 + ch, v);
+            const int nb = n_pos - (cbase + ch);  // columns [0, nb) of this chunk are positive-gamma channels
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
+            if (nb >= 32 || nb <= 0) {
+              stats32(v, s4, q4);
+              const float cs = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+              sum += nb > 0 ? cs : -cs;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float y = __uint_as_float(v[j]);
+                s4[j & 3] += (j < nb) ? y : -y;
+                q4[j & 3] = fmaf(y, y, q4[j & 3]);
+              }
+              sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+            }
+          }
+        }
+        float sq = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+        *stat_mine = make_float2(sum, sq);
+        named_bar(pair_bar, 64);
+        const float2 o = *stat_peer;
+        sum += o.x;
+        sq += o.y;
+        const float mean = sum / (float)c3;
+        rstd = rsqrtf(fmaxf(sq / (float)c3 - mean * mean, 0.f) + ln_eps);
+        nmr = -mean * rstd;
+      }
+      trace_e(310);
+      if (dump.xhat2) {
+        float* d_x2 = dump.xhat2 + (tile * 128 + row) * (int64_t)c3;
+        if (h == 0) dump.rstd2[tile * 128 + row] = rstd;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t t0 = ring(i, half) + lane_off + (uint32_t)(h * cq);
+          const int cbase = half * ch2 + h * cq;
+          for (int ch = 0; ch < cq; ch += 32) {
+            tmem_ld32(t0 + ch, v);
 #pragma unroll
             for (int j4 = 0; j4 < 32; j4 += 4)
-              *reinterpret_cast<float4*>(d_x2 + ch + j4) =
+              *reinterpret_cast<float4*>(d_x2 + cbase + ch + j4) =
                   make_float4(fmaf(__uint_as_float(v[j4]), rstd, nmr), fmaf(__uint_as_float(v[j4 + 1]), rstd, nmr),
                               fmaf(__uint_as_float(v[j4 + 2]), rstd, nmr), fmaf(__uint_as_float(v[j4 + 3]), rstd, nmr));
           }
           tc_fence_before();
-          mbar_arrive(BAR(11 + s));
-          continue;
+          mbar_arrive(BAR((half ? DB : DA) + (i & 1)));
         }
-        named_bar(1 + s, 256);  // previous tile's combine has finished reading wkey
-        // Max over the warp's 32 points per channel without cross-lane reductions: every lane packs
-        // (value bits & ~31) | (31 - lane) -- the low 5 mantissa bits carry the lane so ties resolve to the
-        // smallest point index -- writes its 32 keys as one row of a warp-private 32x32 tile (XOR-swizzled
-        // float4 chunks, conflict-free) in the slot's idle activation buffer, then reads back one COLUMN.
-        // Padding rows (n >= N) are staged as copies of the cloud's point 0, so they can only tie with a
-        // real point and the smallest-index rule drops them: no masking.  ReLU commutes with max, so it is
-        // applied once per (cloud, channel) in the finalize kernel; here keys are compared as SIGNED ints
-        // (any positive float beats any negative one; the order among negatives is irrelevant after ReLU).
-        uint32_t* tr = reinterpret_cast<uint32_t*>(act) + (h * 4 + q) * 1024;  // 4 KB per warp
-        const uint32_t lane_tag = 31u - (uint32_t)lane;
-        uint32_t st_off[8], ld_off[8];  // XOR-swizzled word offsets, hoisted out of the chunk loop
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          st_off[k] = (uint32_t)(lane * 32 + ((k ^ (lane & 7)) << 2));
-          ld_off[k] = (uint32_t)((((lane >> 2) ^ k) << 2) + (lane & 3));
-        }
-        uint32_t v[32];
-        for (int ch = col0; ch < col0 + (c3 >> 1); ch += 32) {
+        continue;
+      }
+      named_bar(1, 256);  // previous tile's combine has finished reading wkey
+      // Max over the warp's 32 points per channel without cross-lane reductions: every lane packs
+      // (bits(z + 16) & ~31) | (31 - lane), z = sign(g2) * xhat -- z + 16 is a positive float, so integer order is
+      // value order, and the low 5 mantissa bits carry the lane so ties resolve to the smallest point index --
+      // writes its 32 keys as one row of a warp-private 32x32 tile (XOR-swizzled float4 chunks, conflict-free), then
+      // reads back one COLUMN.  Padding rows (n >= N) are staged as copies of the cloud's point 0, so they can only
+      // tie with a real point and the smallest-index rule drops them: no masking.  |g2|, b2 and the ReLU are applied
+      // once per (cloud, channel) in the finalize kernel (they commute with the max).
+      const float add_pos = nmr + kKeyBias, add_neg = kKeyBias - nmr;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const uint32_t t0 = ring(i, half) + lane_off + (uint32_t)(h * cq);
+        const int cbase = half * ch2 + h * cq;
+        for (int ch = 0; ch < cq; ch += 32) {
           if (dbg & 1) break;
-          tmem_ld32(tlane + ch, v);
+          tmem_ld32(t0 + ch, v);
+          const int nb = n_pos - (cbase + ch);
+          if (nb >= 32 || nb <= 0) {
+            const float add = nb > 0 ? add_pos : add_neg;
 #pragma unroll
-          for (int j4 = 0; j4 < 32; j4 += 4) {
-            const float4 gg = *reinterpret_cast<const float4*>(g2 + ch + j4);
-            const float4 bb = *reinterpret_cast<const float4*>(be2 + ch + j4);
-            const float gv[4] = {gg.x, gg.y, gg.z, gg.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+            for (int j = 0; j < 32; ++j)
+              asm("lop3.b32 %0, %1, 0xffffffe0, %2, 0xea;"  // (z & ~31) | tag
+                  : "=r"(v[j])
+                  : "r"(__float_as_uint(fmaf(__uint_as_float(v[j]), rstd, add))), "r"(lane_tag));
+          } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float o = fmaf(fmaf(__uint_as_float(v[j4 + e]), rstd, nmr), gv[e], bv[e]);
-              v[j4 + e] = (__float_as_uint(o) & ~31u) | lane_tag;
-            }
+            for (int j = 0; j < 32; ++j)
+              asm("lop3.b32 %0, %1, 0xffffffe0, %2, 0xea;"
+                  : "=r"(v[j])
+                  : "r"(__float_as_uint(fmaf(__uint_as_float(v[j]), rstd, (j < nb) ? add_pos : add_neg))), "r"(lane_tag));
           }
           __syncwarp();  // previous chunk's column reads are done
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4)
             *reinterpret_cast<uint4*>(tr + st_off[c4]) = make_uint4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
           __syncwarp();
-          int m0 = INT_MIN, m1 = INT_MIN;  // two independent max chains
+          uint32_t m0 = 0, m1 = 0;  // two independent max chains
 #pragma unroll
           for (int p = 0; p < 32; p += 4) {
-            m0 = __vimax3_s32(m0, (int)tr[p * 32 + ld_off[p & 7]], (int)tr[(p + 1) * 32 + ld_off[(p + 1) & 7]]);
-            m1 = __vimax3_s32(m1, (int)tr[(p + 2) * 32 + ld_off[(p + 2) & 7]], (int)tr[(p + 3) * 32 + ld_off[(p + 3) & 7]]);
+            m0 = __vimax3_u32(m0, tr[p * 32 + ld_off[p & 7]], tr[(p + 1) * 32 + ld_off[(p + 1) & 7]]);
+            m1 = __vimax3_u32(m1, tr[(p + 2) * 32 + ld_off[(p + 2) & 7]], tr[(p + 3) * 32 + ld_off[(p + 3) & 7]]);
           }
-          const uint32_t m = (uint32_t)max(m0, m1);
-          // lane now owns channel ch + lane: m = max key over this warp's 32 points.  Flipping the sign bit
-          // turns the signed order into an unsigned one for the packed u64 atomicMax across warps / tiles.
-          const uint32_t idx = (uint32_t)((int)(tile % tiles_per_cloud) * 128 + q * 32) + (31u - (m & 31u));
-          wkey[ch + lane] = ((unsigned long long)((m & ~31u) ^ 0x80000000u) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+          const uint32_t m = max(m0, m1);
+          // lane now owns (permuted) channel cbase + ch + lane: m = max key over this warp's 32 points
+          const uint32_t idx = idx_base + (31u - (m & 31u));
+          wkey[cbase + ch + lane] = ((unsigned long long)(m & ~31u) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
         }
         tc_fence_before();
-        mbar_arrive(BAR(11 + s));  // accumulator drained: the MMA warp may start this slot's next tile
-        named_bar(1 + s, 256);
-        for (int c = tid_slot; c < c3; c += 256) {
-          unsigned long long k = wkey_slot[c];
-          k = max(k, wkey_slot[c3 + c]);
-          k = max(k, wkey_slot[2 * c3 + c]);
-          k = max(k, wkey_slot[3 * c3 + c]);
-          atomicMax(pool_keys + (int64_t)cloud * c3 + c, k);
-        }
+        mbar_arrive(BAR((half ? DB : DA) + (i & 1)));  // ring slot drained: the next tile's MMA may overwrite it
+      }
+      trace_e(400);
+      named_bar(1, 256);
+      for (int c = tid_grp; c < c3; c += 256) {
+        unsigned long long k = wkey_all[c];
+        k = max(k, wkey_all[c3 + c]);
+        k = max(k, wkey_all[2 * c3 + c]);
+        k = max(k, wkey_all[3 * c3 + c]);
+        atomicMax(pool_keys + (int64_t)cloud * c3 + c, k);
       }
     }
   }
@@ -543,12 +669,18 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
   }
 }
 
-__global__ void pool_finalize_kernel(const unsigned long long* __restrict__ keys, int64_t n, float* __restrict__ pooled,
+// pooled[r][c] = relu(|g2[c]| * max_p z + b2[c]) and the argmax, from the packed (key, ~index) maxima stored at the
+// permuted channel position pos[c]
+__global__ void pool_finalize_kernel(const unsigned long long* __restrict__ keys, int R, int c3,
+                                     const float* __restrict__ g2, const float* __restrict__ be2,
+                                     const int* __restrict__ pos, float* __restrict__ pooled,
                                      int32_t* __restrict__ argmax) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const unsigned long long k = keys[i];
-  pooled[i] = fmaxf(__uint_as_float((uint32_t)(k >> 32) ^ 0x80000000u), 0.f);  // undo the sign flip; ReLU after max
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)R * c3) return;
+  const int r = (int)(i / c3), c = (int)(i % c3);
+  const unsigned long long k = keys[(int64_t)r * c3 + pos[c]];
+  const float z = __uint_as_float((uint32_t)(k >> 32)) - kKeyBias;
+  pooled[i] = fmaxf(fmaf(fabsf(g2[c]), z, be2[c]), 0.f);
   if (argmax) argmax[i] = (int32_t)(0xFFFFFFFFu - (uint32_t)k);
 }
 
@@ -569,11 +701,30 @@ __device__ __forceinline__ uint32_t img_off(int n, int k, int K) {
   return (uint32_t)((n >> 3) * (K * 16) + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2);
 }
 
-__global__ void pack_weights_kernel(const float* __restrict__ w0, const float* __restrict__ b0,
-                                    const float* __restrict__ w1, const float* __restrict__ g1,
-                                    const float* __restrict__ be1, const float* __restrict__ w2,
-                                    const float* __restrict__ g2, const float* __restrict__ be2, int C, int c1, int c2,
-                                    int c3, int rgb_u8, char* __restrict__ out) {
+__global__ void __launch_bounds__(256)
+pack_weights_kernel(const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w1,
+                    const float* __restrict__ g1, const float* __restrict__ be1, const float* __restrict__ w2,
+                    const float* __restrict__ g2, const float* __restrict__ be2, int C, int c1, int c2, int c3,
+                    int rgb_u8, char* __restrict__ out) {
+  // every block derives the channel permutation of layer 2 (g2 >= 0 first, stable): c3 <= 256 = blockDim
+  __shared__ int s_pos[256];
+  __shared__ int s_npos;
+  {
+    const int c = threadIdx.x;
+    if (c < c3) {
+      int before_same = 0, n_pos = 0;
+      const bool mine = g2[c] >= 0.f;
+      for (int o = 0; o < c3; ++o) {
+        const bool p = g2[o] >= 0.f;
+        n_pos += p;
+        if (o < c && p == mine) ++before_same;
+      }
+      s_pos[c] = mine ? before_same : n_pos + before_same;
+      if (c == 0) s_npos = n_pos;
+    }
+  }
+  __syncthreads();
+  const WpackLayout W = make_wpack(c1, c2, c3);
   const int n0 = c1 * 16, n1 = c2 * c1, n2 = c3 * c2, n3 = 2 * c2 + 2 * c3;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n0) {
@@ -587,13 +738,15 @@ __global__ void pack_weights_kernel(const float* __restrict__ w0, const float* _
     } else if (k <= C + 3) {
       v = w0[n * C + (k - C - 1)];  // lo parts of xyz see the same weights
     }
-    *reinterpret_cast<__nv_bfloat16*>(out + img_off(n, k, 16)) = __float2bfloat16(v);
+    *reinterpret_cast<__nv_bfloat16*>(out + W.w0 + img_off(n, k, 16)) = __float2bfloat16(v);
   } else if (i < n0 + n1) {
     const int e = i - n0, n = e / c1, k = e % c1;
-    *reinterpret_cast<__nv_bfloat16*>(out + c1 * 32 + img_off(n, k, c1)) = __float2bfloat16(w1[e]);
+    *reinterpret_cast<__nv_bfloat16*>(out + W.w1 + img_off(n, k, c1)) = __float2bfloat16(w1[e]);
   } else if (i < n0 + n1 + n2) {
     const int e = i - n0 - n1, n = e / c2, k = e % c2;
-    *reinterpret_cast<__nv_bfloat16*>(out + c1 * 32 + c2 * c1 * 2 + img_off(n, k, c2)) = __float2bfloat16(w2[e]);
+    const float v = w2[e];
+    *reinterpret_cast<__nv_bfloat16*>(out + W.w2 + img_off(n, k, c2)) = __float2bfloat16(v);
+    *reinterpret_cast<__nv_bfloat16*>(out + W.w2s + img_off(s_pos[n], k, c2)) = __float2bfloat16(g2[n] >= 0.f ? v : -v);
   } else if (i < n0 + n1 + n2 + n3) {
     const int e = i - n0 - n1 - n2;
     float v;
@@ -601,15 +754,20 @@ __global__ void pack_weights_kernel(const float* __restrict__ w0, const float* _
     else if (e < 2 * c2) v = be1[e - c2];
     else if (e < 2 * c2 + c3) v = g2[e - 2 * c2];
     else v = be2[e - 2 * c2 - c3];
-    reinterpret_cast<float*>(out + c1 * 32 + c2 * c1 * 2 + c3 * c2 * 2)[e] = v;
+    reinterpret_cast<float*>(out + W.prm)[e] = v;
+  } else if (i < n0 + n1 + n2 + n3 + c3) {
+    const int c = i - (n0 + n1 + n2 + n3);
+    reinterpret_cast<int*>(out + W.pos)[c] = s_pos[c];
+    if (c == 0) *reinterpret_cast<int*>(out + W.npos) = s_npos;
   }
 }
 
 static bool shapes_ok(int c1, int c2, int c3) {
   auto ok = [](int c, int m) { return c >= m && c <= 256 && c % m == 0; };
-  // every layer's channels split into two halves of whole 32-column chunks; the activation buffer doubles as
-  // the 32 KB max-pool transpose scratch (8 warps x 4 KB): needs max(c1, c2) >= 128
-  return ok(c1, 64) && ok(c2, 64) && ok(c3, 64) && (c1 >= 128 || c2 >= 128) && make_layout(c1, c2, c3).total <= 227 * 1024;
+  // TMEM: max(c1,c2) columns for layers 0/1 plus a ring of three c3/2-column half-accumulators for layer 2;
+  // channels are split between warp pairs in whole 32-column chunks (layers 0/1: halves, layer 2: quarters)
+  return ok(c1, 64) && ok(c2, 64) && ok(c3, 128) && std::max(c1, c2) + 3 * (c3 / 2) <= 512 &&
+         make_layout(c1, c2, c3).total <= 227 * 1024;
 }
 
 // Recompute of the compacted active points on the fused tensor-core kernel (called by pcrl_pointnet_bwd in fast mode):
@@ -655,20 +813,18 @@ int pcrl_debug_get_trace(long long* out_host, int max_events) {
   return 3 * 512;
 }
 
-int64_t pcrl_pointnet_wpack_bytes(int c1, int c2, int c3) {
-  return (int64_t)c1 * 32 + (int64_t)c2 * c1 * 2 + (int64_t)c3 * c2 * 2 + (2 * c2 + 2 * c3) * 4;
-}
+int64_t pcrl_pointnet_wpack_bytes(int c1, int c2, int c3) { return (int64_t)tc::make_wpack(c1, c2, c3).total; }
 
 int pcrl_pointnet_pack_weights(const float* w0, const float* b0, const float* w1, const float* g1, const float* be1,
                                const float* w2, const float* g2, const float* be2, int C, int c1, int c2, int c3,
                                int rgb_u8, void* wpack, void* stream) {
   PCRL_CHECK_ARG(w0 && b0 && w1 && g1 && be1 && w2 && g2 && be2 && wpack);
   if (C + 4 > 16 || !tc::shapes_ok(c1, c2, c3)) {
-    set_error("pcrl_pointnet_pack_weights: shape unsupported by the tcgen05 path (C=%d <= 12, widths (%d,%d,%d) multiples of 64 "
-              "in [64,256] with max(c1,c2) >= 128); use the fp32 path", C, c1, c2, c3);
+    set_error("pcrl_pointnet_pack_weights: shape unsupported by the tcgen05 path (C=%d <= 12, widths (%d,%d,%d) multiples of 64/64/128 "
+              "up to 256 with max(c1,c2) + 1.5*c3 <= 512 TMEM columns); use the fp32 path", C, c1, c2, c3);
     return PCRL_EUNSUPPORTED;
   }
-  const int n = c1 * 16 + c2 * c1 + c3 * c2 + 2 * c2 + 2 * c3;
+  const int n = c1 * 16 + c2 * c1 + c3 * c2 + 2 * c2 + 2 * c3 + c3;
   tc::pack_weights_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(w0, b0, w1, g1, be1, w2, g2, be2, C,
                                                                                    c1, c2, c3, rgb_u8, (char*)wpack);
   PCRL_CHECK_LAUNCH();
@@ -679,7 +835,7 @@ int pcrl_pointnet_fwd_bf16(const void* xh, int R, int N, int NP, const void* wpa
                            float ln_eps, uint64_t* pool_keys, float* pooled, int32_t* argmax, void* stream) {
   PCRL_CHECK_ARG(xh && wpack && pool_keys && pooled && R >= 0 && N > 0 && NP >= N && NP % 128 == 0);
   if (!tc::shapes_ok(c1, c2, c3)) {
-    set_error("pcrl_pointnet_fwd_bf16: widths (%d,%d,%d) unsupported (multiples of 32 in [32,256], smem budget)", c1,
+    set_error("pcrl_pointnet_fwd_bf16: widths (%d,%d,%d) unsupported (multiples of 64/64/128 up to 256, max(c1,c2) + 1.5*c3 <= 512, smem budget)", c1,
               c2, c3);
     return PCRL_EUNSUPPORTED;
   }
@@ -702,8 +858,11 @@ int pcrl_pointnet_fwd_bf16(const void* xh, int R, int N, int NP, const void* wpa
                                                                   (unsigned long long*)pool_keys, tc::DumpOut{});
   PCRL_CHECK_LAUNCH();
   const int64_t n = (int64_t)R * c3;
-  tc::pool_finalize_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>((const unsigned long long*)pool_keys, n, pooled,
-                                                                   argmax);
+  const tc::WpackLayout W = tc::make_wpack(c1, c2, c3);
+  const float* prm = reinterpret_cast<const float*>((const char*)wpack + W.prm);
+  tc::pool_finalize_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(
+      (const unsigned long long*)pool_keys, R, c3, prm + 2 * c2, prm + 2 * c2 + c3,
+      reinterpret_cast<const int*>((const char*)wpack + W.pos), pooled, argmax);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }

@@ -25,7 +25,8 @@ def test_library_exports_every_declared_symbol():
     assert L.cdll.pcrl_abi_version() == 1
     assert isinstance(L.last_error(), str)
     # pure-host queries work without a GPU
-    assert L.pointnet_wpack_bytes(128, 128, 256) == 128 * 32 + 128 * 128 * 2 + 256 * 128 * 2 + (256 + 512) * 4
+    img = 128 * 32 + 128 * 128 * 2 + 256 * 128 * 2 + (256 + 512) * 4  # W0' | W1 | signed/permuted W2 | LN parameters
+    assert L.pointnet_wpack_bytes(128, 128, 256) == img + 256 * 4 + 16 + 256 * 128 * 2  # + permutation, n_pos, plain W2
     assert L.pointnet_fwd_f32_workspace(2, 1280, 128, 128, 256) == 2 * 1280 * 512 * 4
     assert L.pointnet_bwd_workspace(4, 256, 128, 128, 256, 8) > 0
 

@@ -29,14 +29,14 @@ def run(flags, iters=10):
         ts.append(e0.elapsed_time(e1))
     return float(np.mean(ts[3:]))
 tiles = R * spec.NP // 128
-for flags, name in [(0, "full"), (0, "full"), (512, "full, stats passes with x64 TMEM loads"), (1, "no L2 pass-2"), (1 + 512, "no L2 pass-2, x64 stats"),
+for flags, name in [(0, "full"), (0, "full"), (8, "EXPERIMENT: no gamma/beta in L2 pass-2 (wrong results)"), (1, "no L2 pass-2"), 
                     (5, "no L2 epilogue at all"), (5 + 32 + 64, "sync skeleton + MMA")]:
     ms = run(flags)
     print(f"flags {flags:2d} {name:55s} {ms*1e3:8.1f} us   {ms*1e-3*1.9e9/ (tiles/148):8.0f} cyc/tile")
 L.cdll.pcrl_debug_set_fwd_flags(ctypes.c_int(0))
 
 # ---- round-trip trace of CTA 0 (clock64): skeleton mode and full mode
-for flags in ():
+for flags in ((101 + 128, 128) if os.environ.get('PCRL_TRACE') else ()):
     L.cdll.pcrl_debug_set_fwd_flags(ctypes.c_int(flags))
     L.pointnet_fwd_bf16(eng.w["xh_next"], R, spec.n_points, spec.NP, eng.w["wpack"], c1, c2, c3, spec.ln_eps,
                         eng.w["pool_keys_next"], eng.w["pooled_next"], None, st)
@@ -46,5 +46,7 @@ for flags in ():
     ev = sorted([(buf[2 * i + 1], buf[2 * i]) for i in range(n) if buf[2 * i + 1] != 0])
     t0 = ev[0][0]
     print(f"--- trace flags={flags}: {n} events; (cycles since first, event) 1xx=MMA ready-detected 2xx=MMA committed 3xx=epilogue woke 4xx=epilogue arrived; tens digit = slot, units = layer")
-    print(" ".join(f"{t - t0}:{e}" for t, e in ev[40:110]))
+    prev = {}
+    for t, e in ev[60:150]:
+        print(f"{t - t0:8d} {e}")
 L.cdll.pcrl_debug_set_fwd_flags(ctypes.c_int(0))
