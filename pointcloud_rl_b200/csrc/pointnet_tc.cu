@@ -293,7 +293,11 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (dump.rows_dev) n_tiles = min(n_tiles, (*dump.rows_dev + 127) >> 7);  // compacted set: size known on the device only
-  const int n_local = max((n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x, 0);
+  // every CTA takes a contiguous range of tiles: consecutive tiles belong to the same cloud, so the pool group keeps a
+  // running per-cloud maximum in shared memory and touches global memory only when the cloud changes
+  const int t_q = n_tiles / (int)gridDim.x, t_r = n_tiles % (int)gridDim.x;
+  const int n_local = t_q + ((int)blockIdx.x < t_r ? 1 : 0);
+  const int64_t tile0 = (int64_t)blockIdx.x * t_q + min((int)blockIdx.x, t_r);
   const uint32_t wbytes = (uint32_t)(c1 * 32 + c2 * c1 * 2 + c3 * c2 * 2 + (2 * c2 + 2 * c3) * 4);
   const int dbg = g_dbg;
   const int ch2 = c3 >> 1;                                   // channels per layer-2 half
@@ -325,7 +329,7 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
         const int st = i % kStages;
         if (i >= kStages) mbar_wait_relaxed(BAR(XE + st), ((i / kStages) - 1) & 1, 100);
         mbar_expect_tx(BAR(XF + st), kTileBytes);
-        const int64_t tile = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
+        const int64_t tile = tile0 + i;
         bulk_g2s(sbase + L.xst + st * kTileBytes, xh + tile * kTileBytes, kTileBytes, BAR(XF + st));
       }
     }
@@ -401,7 +405,7 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
     const int pair_bar = 6 + q;
     mbar_wait(BAR(WB), 0);  // LN parameters landed
     for (int i = 0; i < n_local; ++i) {
-      const int64_t tile = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
+      const int64_t tile = tile0 + i;
       uint32_t v[32];
       // ---- layer 0: ReLU -> bf16 operand of layer 1
       mbar_wait(BAR(F0), i & 1);
@@ -532,8 +536,27 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
       ld_off[k] = (uint32_t)((((lane >> 2) ^ k) << 2) + (lane & 3));
     }
 
+    // flush: combine the four quadrants' running maxima of `cloud` into global memory and clear them
+    auto flush = [&](int cloud) {
+      named_bar(1, 256);
+      for (int c = tid_grp; c < c3; c += 256) {
+        unsigned long long k = wkey_all[c];
+        k = max(k, wkey_all[c3 + c]);
+        k = max(k, wkey_all[2 * c3 + c]);
+        k = max(k, wkey_all[3 * c3 + c]);
+        atomicMax(pool_keys + (int64_t)cloud * c3 + c, k);
+      }
+      for (int c = tid_grp; c < 4 * c3; c += 256) reinterpret_cast<unsigned long long*>(smem + L.wkey)[c] = 0ull;
+      named_bar(1, 256);
+    };
+    if (!dump.xhat2) {
+      for (int c = tid_grp; c < 4 * c3; c += 256) reinterpret_cast<unsigned long long*>(smem + L.wkey)[c] = 0ull;
+      named_bar(1, 256);
+    }
+    int cur_cloud = n_local > 0 ? (int)(tile0 / tiles_per_cloud) : 0;
+
     for (int i = 0; i < n_local; ++i) {
-      const int64_t tile = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
+      const int64_t tile = tile0 + i;
       const int cloud = (int)(tile / tiles_per_cloud);
       const uint32_t idx_base = (uint32_t)((int)(tile % tiles_per_cloud) * 128 + q * 32);
       mbar_wait(BAR(F2), i & 1);
@@ -599,7 +622,10 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
         }
         continue;
       }
-      named_bar(1, 256);  // previous tile's combine has finished reading wkey
+      if (cloud != cur_cloud) {
+        flush(cur_cloud);
+        cur_cloud = cloud;
+      }
       // Max over the warp's 32 points per channel without cross-lane reductions: every lane packs
       // (bits(z + 16) & ~31) | (31 - lane), z = sign(g2) * xhat -- z + 16 is a positive float, so integer order is
       // value order, and the low 5 mantissa bits carry the lane so ties resolve to the smallest point index --
@@ -644,21 +670,16 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
           const uint32_t m = max(m0, m1);
           // lane now owns (permuted) channel cbase + ch + lane: m = max key over this warp's 32 points
           const uint32_t idx = idx_base + (31u - (m & 31u));
-          wkey[cbase + ch + lane] = ((unsigned long long)(m & ~31u) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+          const unsigned long long key = ((unsigned long long)(m & ~31u) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+          unsigned long long* slot = wkey + cbase + ch + lane;  // owned by this lane: running maximum over the cloud's tiles
+          *slot = max(*slot, key);
         }
         tc_fence_before();
         mbar_arrive(BAR((half ? DB : DA) + (i & 1)));  // ring slot drained: the next tile's MMA may overwrite it
       }
       trace_e(400);
-      named_bar(1, 256);
-      for (int c = tid_grp; c < c3; c += 256) {
-        unsigned long long k = wkey_all[c];
-        k = max(k, wkey_all[c3 + c]);
-        k = max(k, wkey_all[2 * c3 + c]);
-        k = max(k, wkey_all[3 * c3 + c]);
-        atomicMax(pool_keys + (int64_t)cloud * c3 + c, k);
-      }
     }
+    if (!dump.xhat2 && n_local > 0) flush(cur_cloud);
   }
 
   tc_fence_before();
