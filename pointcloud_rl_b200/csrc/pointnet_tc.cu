@@ -176,6 +176,31 @@ __device__ __forceinline__ void stats32(const uint32_t (&v)[32], float (&s)[4], 
   }
 }
 
+// Dump-mode store of one 32x32 fp32 chunk.  After tcgen05.ld every thread holds 32 consecutive floats of ITS row, so a
+// direct store makes each instruction touch 32 different lines with 16 bytes each.  The chunk goes through a
+// warp-private 2 KB scratch tile (two 16-column halves, XOR-swizzled 16-byte slots, conflict-free both ways) so that
+// every global store instruction writes eight 64-byte row segments instead.
+// x: this lane's row; g: address of (row 0 of the warp, first column of the chunk) in a row-major array of pitch ld.
+__device__ __forceinline__ void dump_chunk32(float* scratch, float* g, int64_t ld, const uint32_t (&x)[32], int lane) {
+  const int wsw = (lane >> 1) & 3;
+  const int rr = lane >> 2, rs = lane & 3;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    __syncwarp();
+#pragma unroll
+    for (int sl = 0; sl < 4; ++sl)
+      *reinterpret_cast<uint4*>(scratch + lane * 16 + ((sl ^ wsw) << 2)) =
+          make_uint4(x[half * 16 + 4 * sl], x[half * 16 + 4 * sl + 1], x[half * 16 + 4 * sl + 2], x[half * 16 + 4 * sl + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = k * 8 + rr;
+      const float4 val = *reinterpret_cast<const float4*>(scratch + r * 16 + ((rs ^ ((r >> 1) & 3)) << 2));
+      *reinterpret_cast<float4*>(g + r * ld + half * 16 + rs * 4) = val;
+    }
+  }
+}
+
 // "Dump" mode (the sparse backward's recompute): instead of max-pooling, every row's intermediates are written out
 // in fp32 for the LayerNorm / GEMM backward kernels.  rows_dev bounds the compacted rows actually present.
 struct DumpOut {
@@ -403,6 +428,7 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
     float2* stat_mine = reinterpret_cast<float2*>(smem + L.stat) + (2 + h) * 128 + row;
     const float2* stat_peer = reinterpret_cast<const float2*>(smem + L.stat) + (2 + (h ^ 1)) * 128 + row;
     const int pair_bar = 6 + q;
+    float* dscr = reinterpret_cast<float*>(smem + L.tr) + (warp - 4) * 512;  // dump mode: 2 KB of the (idle) max-pool scratch
     mbar_wait(BAR(WB), 0);  // LN parameters landed
     for (int i = 0; i < n_local; ++i) {
       const int64_t tile = tile0 + i;
@@ -412,15 +438,13 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
       tc_fence_after();
       if (!(dbg & 64)) {
         const int col0 = h * (c1 >> 1);
-        float* d_h0 = dump.h0 ? dump.h0 + (tile * 128 + row) * (int64_t)c1 : nullptr;
+        float* d_h0 = dump.h0 ? dump.h0 + (tile * 128 + q * 32) * (int64_t)c1 : nullptr;
         for (int ch = col0; ch < col0 + (c1 >> 1); ch += 32) {
           tmem_ld32(tlane + ch, v);
           if (d_h0) {
 #pragma unroll
-            for (int j4 = 0; j4 < 32; j4 += 4)
-              *reinterpret_cast<float4*>(d_h0 + ch + j4) =
-                  make_float4(fmaxf(__uint_as_float(v[j4]), 0.f), fmaxf(__uint_as_float(v[j4 + 1]), 0.f),
-                              fmaxf(__uint_as_float(v[j4 + 2]), 0.f), fmaxf(__uint_as_float(v[j4 + 3]), 0.f));
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaxf(__uint_as_float(v[j]), 0.f));
+            dump_chunk32(dscr, d_h0 + ch, c1, v, lane);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -460,45 +484,35 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
       }
       if (i > 0) mbar_wait(BAR(F2), (i - 1) & 1);  // both layer-2 MMAs of the previous tile have finished reading h1
       if (!(dbg & 32)) {
-        float* d_x1 = dump.xhat1 ? dump.xhat1 + (tile * 128 + row) * (int64_t)c2 : nullptr;
-        float* d_h1 = dump.h1 ? dump.h1 + (tile * 128 + row) * (int64_t)c2 : nullptr;
+        float* d_x1 = dump.xhat1 ? dump.xhat1 + (tile * 128 + q * 32) * (int64_t)c2 : nullptr;
+        float* d_h1 = dump.h1 ? dump.h1 + (tile * 128 + q * 32) * (int64_t)c2 : nullptr;
         if (d_x1 && h == 0) dump.rstd1[tile * 128 + row] = rstd;
         for (int ch = col0; ch < col0 + (c2 >> 1); ch += 32) {
           tmem_ld32(tlane + ch, v);
-          if (d_x1) {
 #pragma unroll
-            for (int j4 = 0; j4 < 32; j4 += 4) {
-              const float4 gg = *reinterpret_cast<const float4*>(g1 + ch + j4);
-              const float4 bb = *reinterpret_cast<const float4*>(be1 + ch + j4);
-              float4 xh4, hh4;
-              xh4.x = fmaf(__uint_as_float(v[j4]), rstd, nmr);
-              xh4.y = fmaf(__uint_as_float(v[j4 + 1]), rstd, nmr);
-              xh4.z = fmaf(__uint_as_float(v[j4 + 2]), rstd, nmr);
-              xh4.w = fmaf(__uint_as_float(v[j4 + 3]), rstd, nmr);
-              hh4.x = fmaxf(fmaf(xh4.x, gg.x, bb.x), 0.f);
-              hh4.y = fmaxf(fmaf(xh4.y, gg.y, bb.y), 0.f);
-              hh4.z = fmaxf(fmaf(xh4.z, gg.z, bb.z), 0.f);
-              hh4.w = fmaxf(fmaf(xh4.w, gg.w, bb.w), 0.f);
-              *reinterpret_cast<float4*>(d_x1 + ch + j4) = xh4;
-              *reinterpret_cast<float4*>(d_h1 + ch + j4) = hh4;
-            }
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), rstd, nmr));  // xhat
+          if (d_x1) dump_chunk32(dscr, d_x1 + ch, c2, v, lane);
+#pragma unroll
+          for (int j4 = 0; j4 < 32; j4 += 4) {
+            const float4 gg = *reinterpret_cast<const float4*>(g1 + ch + j4);
+            const float4 bb = *reinterpret_cast<const float4*>(be1 + ch + j4);
+            v[j4] = __float_as_uint(fmaf(__uint_as_float(v[j4]), gg.x, bb.x));
+            v[j4 + 1] = __float_as_uint(fmaf(__uint_as_float(v[j4 + 1]), gg.y, bb.y));
+            v[j4 + 2] = __float_as_uint(fmaf(__uint_as_float(v[j4 + 2]), gg.z, bb.z));
+            v[j4 + 3] = __float_as_uint(fmaf(__uint_as_float(v[j4 + 3]), gg.w, bb.w));
+          }
+          if (d_h1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaxf(__uint_as_float(v[j]), 0.f));
+            dump_chunk32(dscr, d_h1 + ch, c2, v, lane);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 ga = *reinterpret_cast<const float4*>(g1 + ch + 8 * j);
-            const float4 gb = *reinterpret_cast<const float4*>(g1 + ch + 8 * j + 4);
-            const float4 ba = *reinterpret_cast<const float4*>(be1 + ch + 8 * j);
-            const float4 bb = *reinterpret_cast<const float4*>(be1 + ch + 8 * j + 4);
-            const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-            const float bbv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-            float o[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = fmaf(fmaf(__uint_as_float(v[8 * j + e]), rstd, nmr), gg[e], bbv[e]);
             uint4 pk;
-            pk.x = pack_relu_bf16x2(o[0], o[1]);
-            pk.y = pack_relu_bf16x2(o[2], o[3]);
-            pk.z = pack_relu_bf16x2(o[4], o[5]);
-            pk.w = pack_relu_bf16x2(o[6], o[7]);
+            pk.x = pack_relu_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+            pk.y = pack_relu_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+            pk.z = pack_relu_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+            pk.w = pack_relu_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
             *reinterpret_cast<uint4*>(dst1 + ((ch >> 3) + j) * 128) = pk;
           }
         }
@@ -603,7 +617,8 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
       }
       trace_e(310);
       if (dump.xhat2) {
-        float* d_x2 = dump.xhat2 + (tile * 128 + row) * (int64_t)c3;
+        float* d_x2 = dump.xhat2 + (tile * 128 + q * 32) * (int64_t)c3;
+        float* dscr = reinterpret_cast<float*>(smem + L.tr) + (warp - 4) * 512;
         if (h == 0) dump.rstd2[tile * 128 + row] = rstd;
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
@@ -612,10 +627,8 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
           for (int ch = 0; ch < cq; ch += 32) {
             tmem_ld32(t0 + ch, v);
 #pragma unroll
-            for (int j4 = 0; j4 < 32; j4 += 4)
-              *reinterpret_cast<float4*>(d_x2 + cbase + ch + j4) =
-                  make_float4(fmaf(__uint_as_float(v[j4]), rstd, nmr), fmaf(__uint_as_float(v[j4 + 1]), rstd, nmr),
-                              fmaf(__uint_as_float(v[j4 + 2]), rstd, nmr), fmaf(__uint_as_float(v[j4 + 3]), rstd, nmr));
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), rstd, nmr));
+            dump_chunk32(dscr, d_x2 + cbase + ch, c3, v, lane);
           }
           tc_fence_before();
           mbar_arrive(BAR((half ? DB : DA) + (i & 1)));
