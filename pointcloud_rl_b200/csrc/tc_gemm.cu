@@ -11,6 +11,13 @@
 //
 // One 128 x BN output tile per CTA (optionally a K-split slice of it): warp 0 = TMA producer,
 // warp 1 = MMA issuer, warps 2-5 = epilogue (TMEM -> registers -> bias/ReLU -> global).
+//
+// Small-M problems (the MLP heads: M = 256..512 rows, K up to 1024) have too few output tiles to fill 148 SMs and a
+// K loop that is a serial chain of shared-memory-operand MMAs on each of them.  Those run in "cluster split-K" mode:
+// a thread-block cluster of S CTAs owns one (wide) output tile, each CTA contracts 1/S of K into its own TMEM
+// accumulator, writes the partial tile to its shared memory, and after a cluster barrier every CTA sums a 128/S-row
+// band of the tile over all S peers through distributed shared memory and applies the epilogue.  No atomics, no
+// global workspace, fixed summation order.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -97,6 +104,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  __syncwarp();  // the single-lane producer / issuer roles rejoin their warps first (.aligned barrier)
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float4 ld_peer_v4(uint32_t saddr, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(saddr), "r"(rank));
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra));
+  return v;
+}
+
 struct Params {
   float* C;
   int64_t ldc;
@@ -107,6 +131,7 @@ struct Params {
   int relu;
   int mode;      // 0 store, 1 C += (owned tile), 2 atomic add (split-K)
   int split_k;
+  int cluster_k;  // > 1: cluster split-K mode (one tile per cluster of cluster_k CTAs, DSMEM reduction)
   int stages;
   const int* k_dev;  // optional device-side bound on the contraction length
   const int* m_dev;  // optional device-side bound on M
@@ -139,9 +164,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int kb_total = (K + BK - 1) / BK;
   const int kb_per = (kb_total + P.split_k - 1) / P.split_k;
   const int nt = (P.N + P.bn - 1) / P.bn, mt = (P.M + BM - 1) / BM;
-  const int total_tiles = nt * mt * P.split_k;
+  const int S = P.cluster_k;
+  const int total_tiles = S > 1 ? (int)blockIdx.x + 1 : nt * mt * P.split_k;  // cluster mode: exactly one tile per CTA
+  const int kb_per_c = (kb_total + S - 1) / S;
   // tile -> (k-split z, M tile, N tile); N fastest so concurrently running CTAs share the same A rows in L2
   auto tile_coords = [&](int t, int& z, int& i0, int& j0, int& kb0, int& nkb) {
+    if (S > 1) {  // the S CTAs of a cluster share tile t / S and take consecutive K slices
+      z = t % S;
+      const int rem = t / S;
+      i0 = (rem / nt) * BM;
+      j0 = (rem % nt) * P.bn;
+      kb0 = z * kb_per_c;
+      nkb = max(min(kb_total, kb0 + kb_per_c) - kb0, 0);
+      return nkb > 0;
+    }
     z = t / (nt * mt);
     const int rem = t - z * nt * mt;
     i0 = (rem / nt) * BM;
@@ -242,6 +278,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_wait(ACC_FULL(buf), (n >> 1) & 1);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)P.bn;
+      if (S > 1) {
+        // partial tile -> shared memory (the pipeline ring is idle now), row pitch bn + 4 floats: conflict-free
+        float* red = reinterpret_cast<float*>(smem) + (size_t)(q * 32 + lane) * (P.bn + 4);
+        for (int c = 0; c < P.bn; c += 32) {
+          tmem_ld32(tbase + c, v);
+#pragma unroll
+          for (int j4 = 0; j4 < 32; j4 += 4)
+            *reinterpret_cast<uint4*>(red + c + j4) = make_uint4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
+        }
+        ++n;
+        continue;
+      }
       for (int c = 0; c < P.bn; c += 32) {
         if (c + 32 <= P.bn) {
           tmem_ld32(tbase + c, v);
@@ -304,6 +352,62 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   }
 
+  if (S > 1) {
+    int z, i0, j0, kb0, nkb;
+    const bool have = tile_coords((int)blockIdx.x, z, i0, j0, kb0, nkb);
+    const int pitch = P.bn + 4;
+    if (!have) {  // empty K slice: contribute zeros
+      for (int e = threadIdx.x; e < BM * pitch / 4; e += kThreads) reinterpret_cast<float4*>(smem)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    cluster_sync_all();  // every CTA's partial tile is in its shared memory
+    const int rows_per = BM / S, c4n = P.bn / 4;
+    const int items = rows_per * c4n;
+    // two output float4s per thread and step, all peers' loads in flight before the first add (remote shared-memory
+    // latency, not bandwidth, bounds this loop)
+    for (int e0 = threadIdx.x; e0 < items; e0 += 2 * kThreads) {
+      float4 part[2][8];
+      uint32_t a[2];
+      int rr[2], cc[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int e = min(e0 + u * kThreads, items - 1);
+        rr[u] = z * rows_per + e / c4n;
+        cc[u] = (e % c4n) * 4;
+        a[u] = sbase + (uint32_t)(rr[u] * pitch + cc[u]) * 4;
+#pragma unroll
+        for (int p = 0; p < 8; ++p)
+          if (p < S) part[u][p] = ld_peer_v4(a[u], (uint32_t)p);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (e0 + u * kThreads >= items) break;
+        float4 acc = part[u][0];
+#pragma unroll
+        for (int p = 1; p < 8; ++p)
+          if (p < S) { acc.x += part[u][p].x; acc.y += part[u][p].y; acc.z += part[u][p].z; acc.w += part[u][p].w; }
+        const int row = i0 + rr[u], col = j0 + cc[u];
+        if (row >= P.M || col >= P.N) continue;
+        float o[4] = {acc.x, acc.y, acc.z, acc.w};
+        float* crow = P.C + (int64_t)row * P.ldc + col;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          if (col + q4 >= P.N) break;
+          float x = o[q4];
+          if (P.bias) x += __ldg(P.bias + col + q4);
+          if (P.relu) x = fmaxf(x, 0.f);
+          if (P.mask && !(__ldg(P.mask + (int64_t)row * P.ldmask + col + q4) > 0.f)) x = 0.f;
+          if (P.mode != 0) x += crow[q4];
+          o[q4] = x;
+        }
+        if (col + 4 <= P.N && (reinterpret_cast<uintptr_t>(crow) & 15) == 0) {
+          *reinterpret_cast<float4*>(crow) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+          for (int q4 = 0; q4 < 4 && col + q4 < P.N; ++q4) crow[q4] = o[q4];
+        }
+      }
+    }
+    cluster_sync_all();  // nobody exits while a peer may still read its shared memory
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -368,11 +472,70 @@ int launch_tc_gemm(const TcGemmArgs& g, cudaStream_t st) {
   else if (g.N <= 64 && bn > 64) bn = 64;
   if (g.b_mn && bn < 32) bn = 32;  // MN-major B is loaded in 32-column boxes
   if (g.bn_hint) bn = g.bn_hint;
+  // cluster split-K for short, wide problems (see the header comment): widest tile the accumulator allows, then as
+  // many K slices as keep every slice >= 2 k-blocks and the grid around one wave
+  int cluster_k = 1;
+  const int64_t kb_total = cdiv(g.K, BK);
+  if (!g.k_dev && !g.m_dev && !g.bn_hint && kb_total >= 16 && kb_total <= 64 && g.N >= 32) {
+    const int bn_w = g.N >= 128 ? 128 : (int)align_up(g.N, 32);
+    const int64_t tiles_w = mt * cdiv(g.N, bn_w);
+    int s_k = 1;
+    // clusters of 4 place freely on the GPCs; clusters of 8 with ~200 KB of shared memory each do not all fit at once
+    while (s_k < 4 && tiles_w * (s_k * 2) <= sms && kb_total / (s_k * 2) >= 4) s_k *= 2;
+    if (s_k >= 2) {
+      cluster_k = s_k;
+      bn = bn_w;
+    }
+  }
   Params P{};
   P.C = g.C; P.ldc = g.ldc; P.bias = g.bias; P.M = g.M; P.N = g.N; P.K = g.K; P.bn = bn; P.a_mn = g.a_mn; P.b_mn = g.b_mn;
   P.relu = g.relu; P.mode = g.mode; P.split_k = g.split_k; P.k_dev = g.k_dev; P.m_dev = g.m_dev;
-  P.mask = g.mask; P.ldmask = g.ldmask;
+  P.mask = g.mask; P.ldmask = g.ldmask; P.cluster_k = cluster_k;
   PCRL_CHECK_ARG(g.split_k >= 1 && (g.split_k == 1 || (g.mode == 2 && !g.relu)));
+  if (cluster_k > 1) {
+    P.split_k = 1;  // the caller's atomic split-K request is served by the cluster instead: C (+)= reduced tile
+    const uint32_t stage_b = BM * BK * 4 + bn * BK * 4;
+    const int64_t kb_slice = cdiv(kb_total, cluster_k);
+    const size_t red_bytes = (size_t)BM * (bn + 4) * 4;
+    int stages = (int)std::min<int64_t>(8, std::max<int64_t>(2, kb_slice));
+    while ((size_t)stages * stage_b < red_bytes) ++stages;
+    while ((size_t)stages * stage_b + 4096 > 220 * 1024 && stages > 2) --stages;
+    if ((size_t)stages * stage_b < red_bytes) {
+      set_error("tc_gemm: cluster split-K tile does not fit shared memory");
+      return PCRL_EINVAL;
+    }
+    P.stages = stages;
+    const size_t smem_c = (size_t)stages * stage_b + 8 * (2 * stages + 5) + 16 + 1024;
+    CUtensorMap ma, mb;
+    bool okm;
+    if (!g.a_mn) okm = make_map(&ma, g.A, g.K, g.M, g.lda, BK, BM, false);
+    else         okm = make_map(&ma, g.A, g.M, g.K, g.lda, 32, BK, true);
+    if (!g.b_mn) okm = okm && make_map(&mb, g.B, g.K, g.N, g.ldb, BK, bn, false);
+    else         okm = okm && make_map(&mb, g.B, g.N, g.K, g.ldb, 32, BK, true);
+    if (!okm) {
+      set_error("tc_gemm: cuTensorMapEncodeTiled failed");
+      return PCRL_ECUDA;
+    }
+    static bool attr_c = false;
+    if (!attr_c) {
+      PCRL_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_c = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(mt * cdiv(g.N, bn) * cluster_k), 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem_c;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cluster_k;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    PCRL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<256>, ma, mb, P));
+    return PCRL_OK;
+  }
   const uint32_t stage_bytes = BM * BK * 4 + bn * BK * 4;
   const int64_t n_tiles = mt * cdiv(g.N, bn) * g.split_k;
   const int64_t kb_max = cdiv(cdiv(g.K, BK), g.split_k);
