@@ -52,14 +52,43 @@ def encoded_points_per_update(w):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock + throttle reasons of one GPU, sampled DURING the timed region by a background thread through NVML
+    (in-process: a polling `nvidia-smi` child per rank takes driver locks often enough to slow the ranks it watches).
+    Falls back to `nvidia-smi -lms` when the NVML binding is missing."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+    PERIOD_S = 0.1
 
     def __init__(self, gpu_index):
         self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.gpu])
+            except Exception:
+                pass
+        return self.gpu
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self._nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}",
                                           "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
@@ -68,11 +97,34 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll_nvml(self):
+        nv = self._nvml
+        flags = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._handle, nv.NVML_CLOCK_SM)))
+                mask = int(get_reasons(self._handle))
+                for name, bit in flags.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.PERIOD_S)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self._nvml is not None:
+            self._stop.set()
+            self._thread.join(timeout=5)
+            return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(self.reasons), "samples": len(self.samples), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -91,7 +143,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -243,8 +295,9 @@ def native_arm(args, w, rank, world, local_rank):
         return
 
     # ---- device-resident throughput (`value`)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler = ClockSampler(local_rank) if rank == 0 else None  # one watcher: rank 0's GPU
+    if sampler:
+        sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches_before = eng.L.launches
@@ -257,7 +310,7 @@ def native_arm(args, w, rank, world, local_rank):
     barrier()
     dev_ms = e0.elapsed_time(e1)
     launches_eager = eng.L.launches - launches_before
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
 
     # ---- end to end through the host-facing path: pinned batch -> H2D -> update -> scalar read-back
     copy_stream = torch.cuda.Stream(device=device)
