@@ -29,18 +29,19 @@ __device__ __forceinline__ float block_max(float v, float* red) {
   return t;
 }
 
-// one thread per row; A is small (<= 64)
-__global__ void tanh_gaussian_fwd_kernel(const float* __restrict__ out, int M, int A, float ls_lo, float ls_hi,
-                                         float scale, float bias, const float* __restrict__ eps_in, uint64_t seed,
-                                         const uint64_t* __restrict__ counter_dev, uint32_t stream_id,
-                                         float* __restrict__ action, int ld_action, float* __restrict__ neglogp,
-                                         float* __restrict__ eps_out) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per row, lanes over the action dimensions (A is small, <= 64): the per-element Philox + Box-Muller +
+// exp/tanh/log chain is ~150 instructions, far too long to serialise A of them in one thread
+__global__ void __launch_bounds__(256)
+tanh_gaussian_fwd_kernel(const float* __restrict__ out, int M, int A, float ls_lo, float ls_hi, float scale,
+                         float bias, const float* __restrict__ eps_in, uint64_t seed,
+                         const uint64_t* __restrict__ counter_dev, uint32_t stream_id, float* __restrict__ action,
+                         int ld_action, float* __restrict__ neglogp, float* __restrict__ eps_out) {
+  const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (m >= M) return;
   const uint64_t cnt = counter_dev ? *counter_dev : 0ull;
   const float half_log_2pi = 0.91893853320467274178f;
   float acc = 0.f;
-  for (int j = 0; j < A; ++j) {
+  for (int j = lane; j < A; j += 32) {
     const float mu = out[(int64_t)m * 2 * A + j];
     const float ls = out[(int64_t)m * 2 * A + A + j];
     const float log_std = fminf(fmaxf(ls, ls_lo), ls_hi);
@@ -63,7 +64,8 @@ __global__ void tanh_gaussian_fwd_kernel(const float* __restrict__ out, int M, i
     acc += logp;
     action[(int64_t)m * ld_action + j] = fmaf(t, scale, bias);
   }
-  neglogp[m] = -acc;
+  acc = warp_sum(acc);
+  if (lane == 0) neglogp[m] = -acc;
 }
 
 // dout[m, j]   = d/dmu      = g_u
@@ -185,7 +187,7 @@ int pcrl_tanh_gaussian_fwd(const float* out, int M, int A, float ls_lo, float ls
                            float* action, int ld_action, float* neglogp, float* eps_out, void* stream) {
   PCRL_CHECK_ARG(out && action && neglogp && eps_out && M >= 0 && A > 0 && ld_action >= A);
   if (M == 0) return PCRL_OK;
-  tanh_gaussian_fwd_kernel<<<(unsigned)cdiv(M, 128), 128, 0, as_stream(stream)>>>(
+  tanh_gaussian_fwd_kernel<<<(unsigned)cdiv((int64_t)M * 32, 256), 256, 0, as_stream(stream)>>>(
       out, M, A, ls_lo, ls_hi, scale, bias, eps, seed, counter_dev, stream_id, action, ld_action, neglogp, eps_out);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
