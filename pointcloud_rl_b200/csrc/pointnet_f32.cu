@@ -8,7 +8,7 @@ namespace pcrl {
 namespace tc {
 int recompute_active_tc(const void* xh, const void* wpack, const int32_t* src, const int* count_dev, int capacity,
                         int c1, int c2, int c3, float ln_eps, void* xha_scratch, float* h0, float* xhat1, float* rstd1,
-                        float* h1, float* xhat2, float* rstd2, cudaStream_t st);
+                        float* h1, float* xhat2, float* rstd2, const float* m1, const float* m2, cudaStream_t st);
 }
 
 // max over the N real points of each cloud, ties -> smallest index (torch.max semantics,
@@ -147,6 +147,44 @@ __global__ void scatter_dpool_kernel(const float* __restrict__ pooled, const int
     int a = slot[(int64_t)r * NP + argmax[e]];
     if (a >= 0) dh2[(int64_t)a * c3 + c] = dpooled[e];
   }
+}
+
+// Layer-2 LayerNorm backward when dout is the max-pool scatter (fast mode).  dout[a][c] = dpooled[r][c] only where point
+// a won channel c of cloud r, and there xhat2[a][c] = (pooled[r][c] - b2[c]) / g2[c] is known from the forward.  Pass 1
+// accumulates the two row means LN backward needs and the (sparse) parameter gradients; the dense part of dy2 is then
+// written by the recompute kernel itself and pass 2 adds the sparse term rstd2 * g2 * dout.
+__global__ void ln2_sparse_stats_kernel(const float* __restrict__ pooled, const int32_t* __restrict__ argmax,
+                                        const float* __restrict__ dpooled, const int32_t* __restrict__ slot,
+                                        const float* __restrict__ g2, const float* __restrict__ be2, int R, int NP, int c3,
+                                        float* __restrict__ m1, float* __restrict__ m2, float* __restrict__ dg2,
+                                        float* __restrict__ dbe2) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)R * c3) return;
+  const float pv = pooled[e], g = dpooled[e];
+  if (!(pv > 0.f) || g == 0.f) return;
+  const int r = (int)(e / c3), c = (int)(e % c3);
+  const int a = slot[(int64_t)r * NP + argmax[e]];
+  if (a < 0) return;
+  const float gam = g2[c];
+  const float xh = gam != 0.f ? (pv - be2[c]) / gam : 0.f;
+  const float t = gam * g / (float)c3;
+  atomicAdd(m1 + a, t);
+  atomicAdd(m2 + a, t * xh);
+  atomicAdd(dg2 + c, g * xh);
+  atomicAdd(dbe2 + c, g);
+}
+__global__ void ln2_sparse_fix_kernel(const float* __restrict__ pooled, const int32_t* __restrict__ argmax,
+                                      const float* __restrict__ dpooled, const int32_t* __restrict__ slot,
+                                      const float* __restrict__ g2, const float* __restrict__ rstd2, int R, int NP, int c3,
+                                      float* __restrict__ dy2) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)R * c3) return;
+  const float g = dpooled[e];
+  if (!(pooled[e] > 0.f) || g == 0.f) return;
+  const int r = (int)(e / c3), c = (int)(e % c3);
+  const int a = slot[(int64_t)r * NP + argmax[e]];
+  if (a < 0) return;
+  dy2[(int64_t)a * c3 + c] += rstd2[a] * g2[c] * g;  // (a, c) pairs are unique: no atomics
 }
 
 __global__ void relu_bwd_rows_kernel(float* __restrict__ dy, const float* __restrict__ y, int width,
@@ -318,7 +356,7 @@ int pcrl_pointnet_fwd_f32(const float* xf, int R, int N, int NP, int CP, int C, 
 // workspace layout of the backward (A = capacity = R*c3 active points at most)
 struct BwdWs {
   int32_t *flag, *slot, *src, *counts, *offsets, *total;
-  float *xa, *h0, *y1hat, *rstd1, *h1, *y2hat, *rstd2, *d2, *d1, *d0;
+  float *xa, *h0, *y1hat, *rstd1, *h1, *y2hat, *rstd2, *d2, *d1, *d0, *m12;
   int64_t bytes;
 };
 static BwdWs carve_bwd(void* base, int R, int NP, int c1, int c2, int c3, int CP) {
@@ -346,6 +384,7 @@ static BwdWs carve_bwd(void* base, int R, int NP, int c1, int c2, int c3, int CP
   w.d2 = (float*)take(A * c3 * 4);
   w.d1 = (float*)take(A * c2 * 4);
   w.d0 = (float*)take(A * c1 * 4);
+  w.m12 = (float*)take(A * 2 * 4);  // fast mode: row means of the sparse layer-2 LN backward
   w.bytes = p - reinterpret_cast<char*>(base);
   return w;
 }
@@ -384,12 +423,24 @@ int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, cons
   PCRL_CHECK_LAUNCH();
 
   // 2. recompute the forward of the active points, keeping what LN backward needs
-  if (xh && wpack) {
+  const bool fast = xh && wpack;
+  float* dy2 = w.d2;
+  if (fast) {
     // fast mode: the same fused tcgen05 kernel that produced the argmax, in dump mode (w.d0 doubles as the
-    // gathered bf16 tile scratch: it is only written at the very end of the backward)
+    // gathered bf16 tile scratch: it is only written at the very end of the backward).  dout2 is the max-pool
+    // scatter, so the layer-2 LN backward collapses: row means from the sparse entries first, the dense part of dy2
+    // written by the recompute kernel in place of xhat2, the sparse term added afterwards (see ln2_sparse_*).
+    float *m1 = w.m12, *m2 = w.m12 + A;
+    PCRL_CHECK_CUDA(cudaMemsetAsync(w.m12, 0, (int64_t)A * 2 * 4, st));
+    const unsigned gpairs = (unsigned)cdiv((int64_t)R * c3, 256);
+    ln2_sparse_stats_kernel<<<gpairs, 256, 0, st>>>(pooled, argmax, dpooled, w.slot, g2, be2, R, NP, c3, m1, m2, dg2, dbe2);
+    PCRL_CHECK_LAUNCH();
+    dy2 = w.y2hat;
     if ((rc = tc::recompute_active_tc(xh, wpack, w.src, w.total, A, c1, c2, c3, ln_eps, w.d0, w.h0, w.y1hat, w.rstd1,
-                                      w.h1, w.y2hat, w.rstd2, st)))
+                                      w.h1, dy2, w.rstd2, m1, m2, st)))
       return rc;
+    ln2_sparse_fix_kernel<<<gpairs, 256, 0, st>>>(pooled, argmax, dpooled, w.slot, g2, w.rstd2, R, NP, c3, dy2);
+    PCRL_CHECK_LAUNCH();
   } else {
   {
     const unsigned grid = (unsigned)cdiv(A, 16);
@@ -402,13 +453,13 @@ int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, cons
   if ((rc = gemm_nt(w.h1, c2, w2, c2, nullptr, 0, w.d2, c3, A, c2, c3, w.total, st, tf32))) return rc;
   // (the post-LN activation of layer 2 itself is not needed: only xhat2 / rstd2)
   if ((rc = launch_ln_rows(w.d2, c3, g2, be2, w.d2, c3, w.y2hat, w.rstd2, A, c3, ln_eps, 1, w.total, st))) return rc;
-  }
 
   // 3. dL/dh2: zero except the argmax entries (ReLU mask holds there: pooled > 0)
   PCRL_CHECK_CUDA(cudaMemsetAsync(w.d2, 0, (int64_t)A * c3 * 4, st));
   scatter_dpool_kernel<<<(unsigned)cdiv((int64_t)R * c3, 256), 256, 0, st>>>(pooled, argmax, dpooled, w.slot, R, NP,
                                                                               c3, w.d2);
   PCRL_CHECK_LAUNCH();
+  }
 
   // The weight-gradient GEMMs only feed the optimizer, the data-gradient chain feeds the next layer: run the
   // wgrads on an internal side stream (event fork/join, graph-capturable) so they overlap the dgrad chain.
@@ -420,16 +471,16 @@ int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, cons
     PCRL_CHECK_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
   }
   // 4. layer 2 backward: LN -> dW2 (side), dh1 (main)
-  if ((rc = launch_ln_rows_bwd(w.d2, c3, w.y2hat, w.rstd2, g2, dg2, dbe2, w.d2, c3, A, c3, w.total, st))) return rc;
+  if (!fast && (rc = launch_ln_rows_bwd(w.d2, c3, w.y2hat, w.rstd2, g2, dg2, dbe2, w.d2, c3, A, c3, w.total, st))) return rc;
   PCRL_CHECK_CUDA(cudaEventRecord(ev_fork, st));
   PCRL_CHECK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
   if (tf32) {  // contraction tails [count, round_up(count, 32)) must be zero for the TMA-fed wgrad GEMMs
-    if ((rc = launch_zero_tail(w.d2, c3, w.total, A, side))) return rc;
+    if ((rc = launch_zero_tail(dy2, c3, w.total, A, side))) return rc;
     if ((rc = launch_zero_tail(w.h1, c2, w.total, A, side))) return rc;
     if ((rc = launch_zero_tail(w.h0, c1, w.total, A, side))) return rc;
   }
-  if ((rc = gemm_tn_acc(w.d2, c3, w.h1, c2, dw2, c2, A, c3, c2, w.total, expect, side, tf32))) return rc;
-  if ((rc = gemm_nn(w.d2, c3, w2, c2, w.d1, c2, A, c3, c2, w.total, st, tf32, w.h1))) return rc;  // ReLU bwd fused
+  if ((rc = gemm_tn_acc(dy2, c3, w.h1, c2, dw2, c2, A, c3, c2, w.total, expect, side, tf32))) return rc;
+  if ((rc = gemm_nn(dy2, c3, w2, c2, w.d1, c2, A, c3, c2, w.total, st, tf32, w.h1))) return rc;  // ReLU bwd fused
   // 5. layer 1 backward: LN -> dW1 (side), dh0 (main)
   if ((rc = launch_ln_rows_bwd(w.d1, c2, w.y1hat, w.rstd1, g1, dg1, dbe1, w.d1, c2, A, c2, w.total, st))) return rc;
   PCRL_CHECK_CUDA(cudaEventRecord(ev_fork, st));

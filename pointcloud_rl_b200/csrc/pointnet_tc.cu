@@ -206,6 +206,11 @@ __device__ __forceinline__ void dump_chunk32(float* scratch, float* g, int64_t l
 struct DumpOut {
   const int* rows_dev;
   float *h0, *xhat1, *rstd1, *h1, *xhat2, *rstd2;
+  // If set, `xhat2` receives the dense part of the layer-2 LayerNorm backward instead of xhat2:
+  //   dy2[a][c] = rstd2[a] * (-m1[a] - xhat2[a][c] * m2[a]),   m1 = mean_c(g2*dout), m2 = mean_c(g2*dout*xhat2)
+  // (dout is nonzero only at the (row, channel) pairs that won the max-pool; their xhat is known from the pooled
+  // value, so m1/m2 exist before the recompute and the separate LN-backward pass over [A, c3] disappears).
+  const float *m1, *m2;
 };
 
 // Packed weight buffer (pcrl_pointnet_pack_weights):
@@ -620,14 +625,22 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
         float* d_x2 = dump.xhat2 + (tile * 128 + q * 32) * (int64_t)c3;
         float* dscr = reinterpret_cast<float*>(smem + L.tr) + (warp - 4) * 512;
         if (h == 0) dump.rstd2[tile * 128 + row] = rstd;
+        const float dm1 = dump.m1 ? dump.m1[tile * 128 + row] : 0.f, dm2 = dump.m1 ? dump.m2[tile * 128 + row] : 0.f;
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
           const uint32_t t0 = ring(i, half) + lane_off + (uint32_t)(h * cq);
           const int cbase = half * ch2 + h * cq;
           for (int ch = 0; ch < cq; ch += 32) {
             tmem_ld32(t0 + ch, v);
+            if (dump.m1) {
+              // rstd * (-m1 - (y*rstd + nmr) * m2) = y * (-rstd^2 m2) + rstd * (-m1 - nmr * m2)
+              const float ka = -rstd * rstd * dm2, kb = rstd * (-dm1 - nmr * dm2);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), rstd, nmr));
+              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), ka, kb));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), rstd, nmr));
+            }
             dump_chunk32(dscr, d_x2 + cbase + ch, c3, v, lane);
           }
           tc_fence_before();
@@ -808,7 +821,7 @@ static bool shapes_ok(int c1, int c2, int c3) {
 // gathers their bf16 tile rows, runs the three layers and writes h0 / xhat1 / rstd1 / h1 / xhat2 / rstd2 (fp32).
 int recompute_active_tc(const void* xh, const void* wpack, const int32_t* src, const int* count_dev, int capacity,
                         int c1, int c2, int c3, float ln_eps, void* xha_scratch, float* h0, float* xhat1, float* rstd1,
-                        float* h1, float* xhat2, float* rstd2, cudaStream_t st) {
+                        float* h1, float* xhat2, float* rstd2, const float* m1, const float* m2, cudaStream_t st) {
   if (!shapes_ok(c1, c2, c3)) {
     set_error("recompute_active_tc: widths unsupported by the tcgen05 path");
     return PCRL_EUNSUPPORTED;
@@ -818,7 +831,7 @@ int recompute_active_tc(const void* xh, const void* wpack, const int32_t* src, c
   const SmemLayout L = make_layout(c1, c2, c3);
   PCRL_CHECK_CUDA(cudaFuncSetAttribute(pointnet_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const int n_tiles = (int)cdiv(capacity, 128);
-  DumpOut d{count_dev, h0, xhat1, rstd1, h1, xhat2, rstd2};
+  DumpOut d{count_dev, h0, xhat1, rstd1, h1, xhat2, rstd2, m1, m2};
   pointnet_fwd_tc_kernel<<<std::min(sm_count(), n_tiles), kThreads, L.total, st>>>(
       (const char*)xha_scratch, (const char*)wpack, n_tiles, /*tiles_per_cloud=*/1 << 30, /*N=*/0, c1, c2, c3, ln_eps, 0,
       nullptr, d);

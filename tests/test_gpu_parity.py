@@ -291,7 +291,8 @@ def test_pointnet_bwd_sparse_matches_autograd(L, tf32):
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
-@pytest.mark.parametrize("M,N,K", [(512, 1024, 1024), (200, 72, 136), (128, 1, 1024), (256, 128, 5000), (37, 300, 64)])
+@pytest.mark.parametrize("M,N,K", [(512, 1024, 1024), (200, 72, 136), (128, 1, 1024), (256, 128, 5000), (37, 300, 64),
+                                   (300, 200, 520), (512, 44, 1024), (130, 1000, 1000)])  # the last three: cluster split-K, ragged
 def test_gemm_tf32_tcgen05(L, a_mn, b_mn, M, N, K):
     """Raw tcgen05 TF32 GEMM against fp64 matmul for every operand-major combination; TF32 keeps 10 mantissa bits."""
     g = torch.Generator().manual_seed(M + N + K)
@@ -331,7 +332,7 @@ def test_gemm_tf32_tcgen05(L, a_mn, b_mn, M, N, K):
     assert rel_err(C3[:, :N], ref) < 2e-3
 
 
-@pytest.mark.parametrize("M,K,N", [(512, 256, 1024), (256, 1024, 1), (64, 236, 44)])
+@pytest.mark.parametrize("M,K,N", [(512, 256, 1024), (256, 1024, 1), (64, 236, 44), (512, 1024, 1024), (300, 520, 200)])
 def test_linear_tf32_path(L, M, K, N):
     g = torch.Generator().manual_seed(3)
     x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K**0.5, torch.randn(N, generator=g)
