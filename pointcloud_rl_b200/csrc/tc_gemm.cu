@@ -158,6 +158,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   auto ACC_FULL = [&](int b) { return bar0 + 8u * (2 * P.stages + b); };
   auto ACC_EMPTY = [&](int b) { return bar0 + 8u * (2 * P.stages + 2 + b); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + (size_t)P.stages * stage_bytes + 8 * (2 * P.stages + 4));
+  const uint32_t epi_off = (uint32_t)(P.stages * stage_bytes + 8 * (2 * P.stages + 5) + 16 + 15) & ~15u;  // 4 x 2 KB epilogue scratch
 
   const int K = P.k_dev ? min(P.K, *P.k_dev) : P.K;
   const int Mlim = P.m_dev ? min(P.M, *P.m_dev) : P.M;
@@ -274,7 +275,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int z, i0, j0, kb0, nkb;
       if (!tile_coords(t, z, i0, j0, kb0, nkb)) continue;
       const uint32_t buf = n & 1;
-      const int row = i0 + q * 32 + lane;
       mbar_wait(ACC_FULL(buf), (n >> 1) & 1);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)P.bn;
@@ -290,6 +290,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         ++n;
         continue;
       }
+      // After tcgen05.ld a thread holds 32 consecutive columns of ITS row: stored directly, every instruction would
+      // touch 32 different rows with 16 bytes each.  Each 32x32 chunk goes through a warp-private, XOR-swizzled 2 KB
+      // scratch tile (two 16-column halves) so that a lane ends up with a float4 of row k*8 + lane/4, columns
+      // (lane%4)*4.. : bias / ReLU / mask / accumulate then run on 64-byte row segments, loads and stores coalesced.
+      float* scr = reinterpret_cast<float*>(smem + epi_off) + q * 512;
+      const int wsw = (lane >> 1) & 3, rr = lane >> 2, rs = lane & 3;
       for (int c = 0; c < P.bn; c += 32) {
         if (c + 32 <= P.bn) {
           tmem_ld32(tbase + c, v);
@@ -303,43 +309,59 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         }
         const int ncol = min(32, P.bn - c);
-        if (row < P.M) {
-          float* crow = P.C + (int64_t)row * P.ldc + j0 + c;
-          const bool vec_ok = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && (j0 + c + ncol <= P.N);
 #pragma unroll
-          for (int j4 = 0; j4 < 32; j4 += 4) {
-            if (j4 >= ncol) break;
-            float o[4];
+        for (int half = 0; half < 2; ++half) {
+          if (half * 16 >= ncol) break;
+          __syncwarp();
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl)
+            *reinterpret_cast<uint4*>(scr + lane * 16 + ((sl ^ wsw) << 2)) =
+                make_uint4(v[half * 16 + 4 * sl], v[half * 16 + 4 * sl + 1], v[half * 16 + 4 * sl + 2], v[half * 16 + 4 * sl + 3]);
+          __syncwarp();
+          const int col = j0 + c + half * 16 + rs * 4;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int r = k * 8 + rr;
+            const int grow = i0 + q * 32 + r;
+            const float4 a4 = *reinterpret_cast<const float4*>(scr + r * 16 + ((rs ^ ((r >> 1) & 3)) << 2));
+            if (grow >= P.M || col >= P.N) continue;
+            float o[4] = {a4.x, a4.y, a4.z, a4.w};
+            float* crow = P.C + (int64_t)grow * P.ldc + col;
+            const bool full = col + 4 <= P.N;
             float mk[4] = {1.f, 1.f, 1.f, 1.f};
             if (P.mask) {
-              const float* mrow = P.mask + (int64_t)row * P.ldmask + j0 + c + j4;
-              if (((reinterpret_cast<uintptr_t>(mrow) & 15) == 0) && (j0 + c + j4 + 4 <= P.N)) {
+              const float* mrow = P.mask + (int64_t)grow * P.ldmask + col;
+              if (full && (reinterpret_cast<uintptr_t>(mrow) & 15) == 0) {
                 const float4 m4 = __ldg(reinterpret_cast<const float4*>(mrow));
                 mk[0] = m4.x; mk[1] = m4.y; mk[2] = m4.z; mk[3] = m4.w;
               } else {
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
-                  if (j0 + c + j4 + e < P.N) mk[e] = __ldg(mrow + e);
+                  if (col + e < P.N) mk[e] = __ldg(mrow + e);
               }
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int col = j0 + c + j4 + e;
-              float x = __uint_as_float(v[j4 + e]);
-              if (P.bias && z == 0 && col < P.N) x += __ldg(P.bias + col);
+              float x = o[e];
+              if (P.bias && z == 0 && col + e < P.N) x += __ldg(P.bias + col + e);
               if (P.relu) x = fmaxf(x, 0.f);
               if (!(mk[e] > 0.f)) x = 0.f;
               o[e] = x;
             }
-            if (P.mode == 0 && vec_ok) {
-              *reinterpret_cast<float4*>(crow + j4) = make_float4(o[0], o[1], o[2], o[3]);
+            if (full && (reinterpret_cast<uintptr_t>(crow) & 15) == 0 && P.mode != 2) {
+              float4 w4 = make_float4(o[0], o[1], o[2], o[3]);
+              if (P.mode == 1) {
+                const float4 old = *reinterpret_cast<const float4*>(crow);
+                w4.x += old.x; w4.y += old.y; w4.z += old.z; w4.w += old.w;
+              }
+              *reinterpret_cast<float4*>(crow) = w4;
             } else {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                if (j0 + c + j4 + e < P.N) {
-                  if (P.mode == 0) crow[j4 + e] = o[e];
-                  else if (P.mode == 1) crow[j4 + e] += o[e];
-                  else atomicAdd(crow + j4 + e, o[e]);
+                if (col + e < P.N) {
+                  if (P.mode == 0) crow[e] = o[e];
+                  else if (P.mode == 1) crow[e] += o[e];
+                  else atomicAdd(crow + e, o[e]);
                 }
               }
             }
@@ -499,13 +521,13 @@ int launch_tc_gemm(const TcGemmArgs& g, cudaStream_t st) {
     const size_t red_bytes = (size_t)BM * (bn + 4) * 4;
     int stages = (int)std::min<int64_t>(8, std::max<int64_t>(2, kb_slice));
     while ((size_t)stages * stage_b < red_bytes) ++stages;
-    while ((size_t)stages * stage_b + 4096 > 220 * 1024 && stages > 2) --stages;
+    while ((size_t)stages * stage_b + 12288 > 224 * 1024 && stages > 2) --stages;
     if ((size_t)stages * stage_b < red_bytes) {
       set_error("tc_gemm: cluster split-K tile does not fit shared memory");
       return PCRL_EINVAL;
     }
     P.stages = stages;
-    const size_t smem_c = (size_t)stages * stage_b + 8 * (2 * stages + 5) + 16 + 1024;
+    const size_t smem_c = (size_t)stages * stage_b + 8 * (2 * stages + 5) + 32 + 8192 + 1024;
     CUtensorMap ma, mb;
     bool okm;
     if (!g.a_mn) okm = make_map(&ma, g.A, g.K, g.M, g.lda, BK, BM, false);
@@ -544,7 +566,7 @@ int launch_tc_gemm(const TcGemmArgs& g, cudaStream_t st) {
   // tall-skinny problems keep the ring small so two CTAs fit on an SM
   const int64_t budget = (n_tiles >= 2 * sms && kb_max <= 8) ? 100 * 1024 : 200 * 1024;
   P.stages = (int)std::min<int64_t>(std::min<int64_t>(8, std::max<int64_t>(3, 2 * kb_max)), std::max<int64_t>(2, budget / stage_bytes));
-  const size_t smem = (size_t)P.stages * stage_bytes + 8 * (2 * P.stages + 5) + 16 + 1024;
+  const size_t smem = (size_t)P.stages * stage_bytes + 8 * (2 * P.stages + 5) + 32 + 8192 + 1024;
   const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / smem));
 
   CUtensorMap ma, mb;
