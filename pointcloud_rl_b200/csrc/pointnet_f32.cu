@@ -36,26 +36,25 @@ __global__ void __launch_bounds__(256) maxpool_points_kernel(const float* __rest
 
 // ---- sparse backward helpers -----------------------------------------------------------------
 
-// flag[r*NP + argmax[r,c]] = 1 for every (r,c) that carries gradient: pooled > 0 (ReLU passes) and
-// dpooled != 0.
-__global__ void mark_active_kernel(const float* __restrict__ pooled, const int32_t* __restrict__ argmax,
-                                   const float* __restrict__ dpooled, int R, int NP, int c3,
-                                   int32_t* __restrict__ flag) {
-  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (int64_t)R * c3) return;
-  if (pooled[e] > 0.f && dpooled[e] != 0.f) {
-    int r = (int)(e / c3);
-    flag[(int64_t)r * NP + argmax[e]] = 1;
-  }
-}
-
-// Per-cloud count of flagged points, then an exclusive scan over clouds (single block), then each
-// cloud writes its compacted slots in ascending point order (deterministic layout).
-__global__ void __launch_bounds__(256) count_active_kernel(const int32_t* __restrict__ flag, int NP,
-                                                           int32_t* __restrict__ counts) {
+// A point carries gradient when it won the max for some channel (r, c) with pooled > 0 (ReLU passes) and
+// dpooled != 0.  slot[r*NP+n] = compacted index (or -1); src[a] = r*NP+n; clouds in order, points ascending
+// (deterministic layout); sizes stay on the device.
+// Fused compaction, two launches instead of memset + five kernels.
+// (1) one block per cloud: clear the cloud's flags, mark the points that carry gradient, count them.
+__global__ void __launch_bounds__(256) mark_count_kernel(const float* __restrict__ pooled, const int32_t* __restrict__ argmax,
+                                                         const float* __restrict__ dpooled, int NP, int c3,
+                                                         int32_t* __restrict__ flag, int32_t* __restrict__ counts) {
   const int r = blockIdx.x;
+  int32_t* f = flag + (int64_t)r * NP;
+  for (int n = threadIdx.x; n < NP; n += blockDim.x) f[n] = 0;
+  __syncthreads();
+  for (int c = threadIdx.x; c < c3; c += blockDim.x) {
+    const int64_t e = (int64_t)r * c3 + c;
+    if (pooled[e] > 0.f && dpooled[e] != 0.f) f[argmax[e]] = 1;
+  }
+  __syncthreads();
   int s = 0;
-  for (int n = threadIdx.x; n < NP; n += blockDim.x) s += flag[(int64_t)r * NP + n];
+  for (int n = threadIdx.x; n < NP; n += blockDim.x) s += f[n];
   __shared__ int red[256];
   red[threadIdx.x] = s;
   __syncthreads();
@@ -65,43 +64,30 @@ __global__ void __launch_bounds__(256) count_active_kernel(const int32_t* __rest
   }
   if (threadIdx.x == 0) counts[r] = red[0];
 }
-
-__global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __restrict__ counts, int R,
-                                                           int32_t* __restrict__ offsets, int32_t* __restrict__ total,
-                                                           int capacity) {
-  // R is a few thousand at most: serial chunks per thread + one block-wide scan
-  __shared__ int part[1024];
-  const int per = (R + 1023) / 1024;
-  const int b0 = threadIdx.x * per, b1 = min(R, b0 + per);
-  int s = 0;
-  for (int i = b0; i < b1; ++i) s += counts[i];
-  part[threadIdx.x] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int run = 0;
-    for (int i = 0; i < 1024; ++i) {
-      int t = part[i];
-      part[i] = run;
-      run += t;
-    }
-    *total = min(run, capacity);
-  }
-  __syncthreads();
-  int run = part[threadIdx.x];
-  for (int i = b0; i < b1; ++i) {
-    offsets[i] = run;
-    run += counts[i];
-  }
-}
-
-// slot[r*NP+n] = compacted index (or -1); src[a] = r*NP+n.  One block per cloud, ordered by n.
-__global__ void __launch_bounds__(256) assign_slots_kernel(const int32_t* __restrict__ flag,
-                                                           const int32_t* __restrict__ offsets, int NP, int capacity,
-                                                           int32_t* __restrict__ slot, int32_t* __restrict__ src) {
+// (2) one block per cloud: its base offset is the sum of the previous clouds' counts (R is at most a few thousand),
+// then slots in ascending point order, and the rows are gathered right away: xa (fp32 staged points) and, in fast
+// mode, the 32-byte bf16 tile rows of the fused kernel's operand image.
+__global__ void __launch_bounds__(256) assign_gather_kernel(const int32_t* __restrict__ flag, const int32_t* __restrict__ counts,
+                                                            int R, int NP, int capacity, int CP, const float* __restrict__ xf,
+                                                            const char* __restrict__ xh, int32_t* __restrict__ slot,
+                                                            int32_t* __restrict__ src, int32_t* __restrict__ total,
+                                                            float* __restrict__ xa, char* __restrict__ xha) {
   const int r = blockIdx.x;
+  __shared__ int red[256];
   __shared__ int warp_tot[8];
   __shared__ int base;
-  if (threadIdx.x == 0) base = offsets[r];
+  int s = 0;
+  for (int i = threadIdx.x; i < r; i += blockDim.x) s += counts[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    base = red[0];
+    if (r == R - 1) *total = min(red[0] + counts[r], capacity);
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int n0 = 0; n0 < NP; n0 += 256) {
@@ -118,7 +104,21 @@ __global__ void __launch_bounds__(256) assign_slots_kernel(const int32_t* __rest
       int a = -1;
       if (fl) {
         a = base + pre + __popc(m & ((1u << lane) - 1));
-        if (a < capacity) src[a] = r * NP + n; else a = -1;
+        if (a < capacity) {
+          const int pidx = r * NP + n;
+          src[a] = pidx;
+          const float4* sx = reinterpret_cast<const float4*>(xf + (int64_t)pidx * CP);
+          float4* dx = reinterpret_cast<float4*>(xa + (int64_t)a * CP);
+          for (int q = 0; q < CP / 4; ++q) dx[q] = sx[q];
+          if (xh) {  // two 16-byte core-matrix rows of the 128x16 bf16 tile image
+            const char* sp_ = xh + (int64_t)(pidx >> 7) * 4096 + ((pidx & 127) >> 3) * 256 + (pidx & 7) * 16;
+            char* dp = xha + (int64_t)(a >> 7) * 4096 + ((a & 127) >> 3) * 256 + (a & 7) * 16;
+            *reinterpret_cast<uint4*>(dp) = *reinterpret_cast<const uint4*>(sp_);
+            *reinterpret_cast<uint4*>(dp + 128) = *reinterpret_cast<const uint4*>(sp_ + 128);
+          }
+        } else {
+          a = -1;
+        }
       }
       slot[(int64_t)r * NP + n] = a;
     }
@@ -126,14 +126,6 @@ __global__ void __launch_bounds__(256) assign_slots_kernel(const int32_t* __rest
     if (threadIdx.x == 0) base += tot;
     __syncthreads();
   }
-}
-
-__global__ void gather_rows_kernel(const float* __restrict__ x, int CP, const int32_t* __restrict__ src,
-                                   const int* __restrict__ count, float* __restrict__ out) {
-  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int a = (int)(e / CP), c = (int)(e % CP);
-  if (a >= *count) return;
-  out[e] = x[(int64_t)src[a] * CP + c];
 }
 
 // dh2[slot(r, argmax[r,c]), c] = dpooled[r,c]  (dh2 zeroed beforehand)
@@ -409,21 +401,16 @@ int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, cons
   const int expect = std::max(1, A * 3 / 4);
   int rc;
 
-  // 1. which points carry gradient; compact them
-  PCRL_CHECK_CUDA(cudaMemsetAsync(w.flag, 0, (int64_t)R * NP * 4, st));
-  mark_active_kernel<<<(unsigned)cdiv((int64_t)R * c3, 256), 256, 0, st>>>(pooled, argmax, dpooled, R, NP, c3, w.flag);
+  // 1. which points carry gradient; compact them and gather their staged rows
+  const bool fast = xh && wpack;
+  mark_count_kernel<<<R, 256, 0, st>>>(pooled, argmax, dpooled, NP, c3, w.flag, w.counts);
   PCRL_CHECK_LAUNCH();
-  count_active_kernel<<<R, 256, 0, st>>>(w.flag, NP, w.counts);
-  PCRL_CHECK_LAUNCH();
-  scan_counts_kernel<<<1, 1024, 0, st>>>(w.counts, R, w.offsets, w.total, A);
-  PCRL_CHECK_LAUNCH();
-  assign_slots_kernel<<<R, 256, 0, st>>>(w.flag, w.offsets, NP, A, w.slot, w.src);
-  PCRL_CHECK_LAUNCH();
-  gather_rows_kernel<<<(unsigned)cdiv((int64_t)A * CP, 256), 256, 0, st>>>(xf, CP, w.src, w.total, w.xa);
+  // (fast mode: w.d0 doubles as the gathered bf16 tile scratch, it is only written at the very end of the backward)
+  assign_gather_kernel<<<R, 256, 0, st>>>(w.flag, w.counts, R, NP, A, CP, xf, fast ? (const char*)xh : nullptr, w.slot,
+                                          w.src, w.total, w.xa, (char*)w.d0);
   PCRL_CHECK_LAUNCH();
 
   // 2. recompute the forward of the active points, keeping what LN backward needs
-  const bool fast = xh && wpack;
   float* dy2 = w.d2;
   if (fast) {
     // fast mode: the same fused tcgen05 kernel that produced the argmax, in dump mode (w.d0 doubles as the
@@ -436,7 +423,7 @@ int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, cons
     ln2_sparse_stats_kernel<<<gpairs, 256, 0, st>>>(pooled, argmax, dpooled, w.slot, g2, be2, R, NP, c3, m1, m2, dg2, dbe2);
     PCRL_CHECK_LAUNCH();
     dy2 = w.y2hat;
-    if ((rc = tc::recompute_active_tc(xh, wpack, w.src, w.total, A, c1, c2, c3, ln_eps, w.d0, w.h0, w.y1hat, w.rstd1,
+    if ((rc = tc::recompute_active_tc(xh, wpack, /*src=*/nullptr, w.total, A, c1, c2, c3, ln_eps, w.d0, w.h0, w.y1hat, w.rstd1,
                                       w.h1, dy2, w.rstd2, m1, m2, st)))
       return rc;
     ln2_sparse_fix_kernel<<<gpairs, 256, 0, st>>>(pooled, argmax, dpooled, w.slot, g2, w.rstd2, R, NP, c3, dy2);

@@ -826,8 +826,10 @@ int recompute_active_tc(const void* xh, const void* wpack, const int32_t* src, c
     set_error("recompute_active_tc: widths unsupported by the tcgen05 path");
     return PCRL_EUNSUPPORTED;
   }
-  gather_xh_kernel<<<(unsigned)cdiv(capacity, 256), 256, 0, st>>>((const char*)xh, src, count_dev, (char*)xha_scratch);
-  PCRL_CHECK_LAUNCH();
+  if (src) {  // src == nullptr: the caller has already gathered the tile rows into xha_scratch
+    gather_xh_kernel<<<(unsigned)cdiv(capacity, 256), 256, 0, st>>>((const char*)xh, src, count_dev, (char*)xha_scratch);
+    PCRL_CHECK_LAUNCH();
+  }
   const SmemLayout L = make_layout(c1, c2, c3);
   PCRL_CHECK_CUDA(cudaFuncSetAttribute(pointnet_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const int n_tiles = (int)cdiv(capacity, 128);
