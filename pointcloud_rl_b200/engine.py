@@ -181,6 +181,8 @@ class UpdateEngine:
         c1, c2, c3 = sp.widths
         h1, h2 = sp.hidden
         u8 = dict(dtype=torch.uint8, device=dev)
+        Kp = (D + S + 3) // 4 * 4
+        self.actor_w0p = torch.zeros(h1, Kp, **f32) if (self.tf32 and Kp != D + S and Kp <= D + S + A) else None
         self.raw = {}
         for which in ("obs", "next_obs"):
             d = {"xyz": torch.zeros(B, 3, N, **f32)}
@@ -345,7 +347,12 @@ class UpdateEngine:
         p, (h1n, h2n) = self.p, self.spec.hidden
         h1, h2 = self.w[f"h1_{keep}"], self.w[f"h2_{keep}"]
         ldx = x.stride(0)
-        self.L.linear_fwd(x, ldx, p[f"{net}.w0"], p[f"{net}.b0"], h1, h1n, M, K, h1n, 1, self.tf32, st)
+        w0 = p[f"{net}.w0"]
+        if net == "actor" and self.actor_w0p is not None:
+            # TMA needs a 16-byte row pitch: the actor's first layer reads a zero-padded copy of its [h, D+S] weight
+            # (the extra input columns are the first action columns of `cat`, multiplied by exact zeros)
+            w0, K = self.actor_w0p, self.actor_w0p.shape[1]
+        self.L.linear_fwd(x, ldx, w0, p[f"{net}.b0"], h1, h1n, M, K, h1n, 1, self.tf32, st)
         self.L.linear_fwd(h1, h1n, p[f"{net}.w1"], p[f"{net}.b1"], h2, h2n, M, h1n, h2n, 1, self.tf32, st)
         self.L.linear_fwd(h2, h2n, p[f"{net}.w2"], p[f"{net}.b2"], out, ldo, M, h2n, nout, 0, self.tf32, st)
 
@@ -408,6 +415,8 @@ class UpdateEngine:
         target_entropy = float(hp.target_entropy) if hp.target_entropy is not None else -float(A)
 
         self._pack_weights(ST())
+        if self.actor_w0p is not None:  # refreshed every update: the parameters may have been written from outside
+            L.copy_cols(p["actor.w0"], D + S, 1, 1, self.actor_w0p, self.actor_w0p.shape[1], 0, sp.hidden[0], D + S, ST())
 
         # ---- branch T (side stream 0): TD target, no grad -- sac.py:108-134 / drq.py:71-87
         s_t = self._fork(0)
