@@ -242,7 +242,7 @@ class UpdateEngine:
         self.w = w
         self._graphs = {}
         self.graph_calls = {}
-        self._side = [torch.cuda.Stream(device=dev) for _ in range(3)] if dev.type == "cuda" else []
+        self._side = [torch.cuda.Stream(device=dev) for _ in range(5)] if dev.type == "cuda" else []
         self._landing = None
 
     # ------------------------------------------------------------------ parameters
@@ -356,18 +356,43 @@ class UpdateEngine:
         self.L.linear_fwd(h1, h1n, p[f"{net}.w1"], p[f"{net}.b1"], h2, h2n, M, h1n, h2n, 1, self.tf32, st)
         self.L.linear_fwd(h2, h2n, p[f"{net}.w2"], p[f"{net}.b2"], out, ldo, M, h2n, nout, 0, self.tf32, st)
 
-    def _mlp_bwd(self, net, x, K, M, dout, lddo, nout, keep, dx, want_w, st, scratch="a"):
+    def _mlp_bwd(self, net, x, K, M, dout, lddo, nout, keep, dx, want_w, st, scratch="a", wstream=None):
+        """Backward of one 3-layer head.  The data-gradient chain (dX of layer 3 -> 2 -> 1) is the critical path; the
+        weight/bias gradients only feed the optimizer, so with `wstream` (a side-stream index) they are enqueued on
+        a forked stream, layer by layer behind the dY they need, and joined at the end."""
         p, g, (h1n, h2n) = self.p, self.g, self.spec.hidden
         h1, h2 = self.w[f"h1_{keep}"], self.w[f"h2_{keep}"]
         w = {"dh1": self.w[f"dh1_{scratch}"], "dh2": self.w[f"dh2_{scratch}"]}
-        gw = (lambda n: g[f"{net}.{n}"]) if want_w else (lambda n: None)
+        L = self.L
+        side = self._side[wstream] if (want_w and wstream is not None) else None
+        main = torch.cuda.current_stream()
+
+        def wgrad(xin, ldx, name, dy, lddy, Kin, Nout_):
+            """dW/db of one layer (dy is complete on the main stream when this is called)."""
+            if not want_w:
+                return
+            if side is None:
+                L.linear_bwd(xin, ldx, p[f"{net}.w{name}"], dy, lddy, g[f"{net}.w{name}"], g[f"{net}.b{name}"], None, 0,
+                             None, 0, M, Kin, Nout_, self.tf32, stream_ptr())
+                return
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                L.linear_bwd(xin, ldx, p[f"{net}.w{name}"], dy, lddy, g[f"{net}.w{name}"], g[f"{net}.b{name}"], None, 0,
+                             None, 0, M, Kin, Nout_, self.tf32, stream_ptr())
+
         # each layer's dX GEMM applies the previous ReLU's backward in its epilogue (mask = saved post-activation)
-        self.L.linear_bwd(h2, h2n, p[f"{net}.w2"], dout, lddo, gw("w2"), gw("b2"), w["dh2"], h2n, h2, h2n, M, h2n, nout,
-                          self.tf32, st)
-        self.L.linear_bwd(h1, h1n, p[f"{net}.w1"], w["dh2"], h2n, gw("w1"), gw("b1"), w["dh1"], h1n, h1, h1n, M, h1n, h2n,
-                          self.tf32, st)
-        self.L.linear_bwd(x, x.stride(0), p[f"{net}.w0"], w["dh1"], h1n, gw("w0"), gw("b0"), dx,
-                          dx.stride(0) if dx is not None else 0, None, 0, M, K, h1n, self.tf32, st)
+        wgrad(h2, h2n, 2, dout, lddo, h2n, nout)
+        L.linear_bwd(h2, h2n, p[f"{net}.w2"], dout, lddo, None, None, w["dh2"], h2n, h2, h2n, M, h2n, nout, self.tf32,
+                     stream_ptr())
+        wgrad(h1, h1n, 1, w["dh2"], h2n, h1n, h2n)
+        L.linear_bwd(h1, h1n, p[f"{net}.w1"], w["dh2"], h2n, None, None, w["dh1"], h1n, h1, h1n, M, h1n, h2n, self.tf32,
+                     stream_ptr())
+        wgrad(x, x.stride(0), 0, w["dh1"], h1n, K, h1n)
+        if dx is not None:
+            L.linear_bwd(x, x.stride(0), p[f"{net}.w0"], w["dh1"], h1n, None, None, dx, dx.stride(0), None, 0, M, K, h1n,
+                         self.tf32, stream_ptr())
+        if side is not None:
+            main.wait_stream(side)
 
     def _adam(self, group, idx, lr, betas, gradsq_slot, polyak, st):
         lo, hi = self.layout.group_range[group]
@@ -457,8 +482,8 @@ class UpdateEngine:
         # ---- critic backward: the two heads in parallel, their feature gradients add (sac.py:141-142)
         s_q = self._fork(2)
         with torch.cuda.stream(s_q):
-            self._mlp_bwd("q1", cat, ld_cat, R, w["dq"][:, 1:], 2, 1, "q1", w["dx1"], True, ST(), "b")
-        self._mlp_bwd("q0", cat, ld_cat, R, w["dq"], 2, 1, "q0", w["dx0"], True, ST(), "a")
+            self._mlp_bwd("q1", cat, ld_cat, R, w["dq"][:, 1:], 2, 1, "q1", w["dx1"], True, ST(), "b", wstream=3)
+        self._mlp_bwd("q0", cat, ld_cat, R, w["dq"], 2, 1, "q0", w["dx0"], True, ST(), "a", wstream=4)
         self._join(s_q)
         q_pending = None
         if self.allreduce is not None:
@@ -516,7 +541,7 @@ class UpdateEngine:
             L.add_cols(da, ld_cat, w["dx1"][:, D + S:], ld_cat, da, ld_cat, B, A, ST())
             L.tanh_gaussian_bwd_dev(w["out_pi"], w["eps_pi"], da, ld_cat, self.alpha_dev, B, A, hp.log_std_bound[0],
                                     hp.log_std_bound[1], hp.head_scale, w["dout"], ST())
-            self._mlp_bwd("actor", cat, D + S, B, w["dout"], 2 * A, 2 * A, "actor", None, True, ST(), "a")
+            self._mlp_bwd("actor", cat, D + S, B, w["dout"], 2 * A, 2 * A, "actor", None, True, ST(), "a", wstream=3)
             if self.allreduce is not None:
                 al_lo, al_hi = self.layout.group_range["alpha"]
                 self.allreduce(self.grads[a_lo:al_hi])  # actor grads | d log_alpha in one message
