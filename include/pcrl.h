@@ -36,6 +36,10 @@ extern "C" {
 #define PCRL_AUG_NONE 0
 #define PCRL_AUG_JITTER 1 /* RandomJitterPoints: xyz += U(lo,hi) per coordinate (pcd_aug.py:307-322) */
 #define PCRL_AUG_ROTZ 2   /* GlobalRotScaleTrans, rot only: one z-angle ~U(lo,hi) per cloud (pcd_aug.py:178-215) */
+#define PCRL_AUG_SHIFT 3  /* GlobalRotScaleTrans, translation only (pn_shift.py): one t ~U(lo,hi)^3 per cloud
+                             (pcd_aug.py:192-197, apply_rot_trans :84-123).  Axes: bits 8..10 of aug_kind select the
+                             shifted axes (x,y,z), 0 = all three -- dm_control/pn_shift.py uses [0.04, 0, 0.04] */
+#define PCRL_AUG_SHIFT_AXES(mask) (PCRL_AUG_SHIFT | ((mask) << 8))
 
 int pcrl_abi_version(void);
 const char* pcrl_last_error(void);

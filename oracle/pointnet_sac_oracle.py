@@ -180,6 +180,12 @@ def aug_rot_z(xyz, angle):
     return torch.einsum("bin,bji->bjn", xyz, rot)
 
 
+def aug_shift(xyz, shift):
+    """GlobalRotScaleTrans (translation only, shift_height=True), pcd_aug.py:192-197 + apply_rot_trans :84-123:
+    xyz [B,3,N] + shift [B,3][..., None]."""
+    return xyz + shift[:, :, None]
+
+
 def _apply_aug(obs, hp, noise, which):
     obs = dict(obs)
     kind = hp.get("aug", None)
@@ -187,6 +193,8 @@ def _apply_aug(obs, hp, noise, which):
         obs["xyz"] = aug_jitter(obs["xyz"], noise[f"jitter_{which}"])
     elif kind == "rot":
         obs["xyz"] = aug_rot_z(obs["xyz"], noise[f"angle_{which}"])
+    elif kind == "shift":
+        obs["xyz"] = aug_shift(obs["xyz"], noise[f"shift_{which}"])
     elif kind is not None:
         raise ValueError(kind)
     return obs
@@ -286,7 +294,7 @@ def update(state, batch, updates, hp, noise, capture=None):
 
     batch: dict(obs=dict, next_obs=dict, actions [B,A], rewards [B,1], dones [B,1]) of numpy / torch.
     noise: injected randomness -- jitter_obs / jitter_next [B*num_aug,3,N] (or angle_obs / angle_next
-           [B*num_aug,1]), eps_next [B*num_aug,A], eps_pi [B,A].
+           [B*num_aug,1], or shift_obs / shift_next [B*num_aug,3]), eps_next [B*num_aug,A], eps_pi [B,A].
     Mutates `state` in place, returns the reference's scalar dict.  `capture` (a dict) receives
     intermediates for the parity tests.
     """

@@ -50,40 +50,64 @@ class RandomJitterPoints(BaseAugmentation):
 
 @AUGMENTATIONS.register_module()
 class GlobalRotScaleTrans(BaseAugmentation):
-    """Per-cloud z-rotation by U(rot_range) (pcd_aug.py:126-215).  Rotation-only subset (`pn_rot.py`);
-    scaling / translation raise (SURVEY.md section 8f lists them as the next widening step)."""
-
-    kind = "rot"
+    """Per-cloud rigid augmentation (pcd_aug.py:126-215).  Supported forms: rotation only about z by U(rot_range)
+    (`pn_rot.py`) and translation only by U(-t, t) per axis with `shift_height=True` (`pn_shift.py`; the enabled axes
+    must share one magnitude, e.g. [0.1, 0.1, 0.1] or [0.04, 0, 0.04]).  Scaling, rotation+translation and the
+    `shift_height=False` quirk (the reference zeroes the LAST CLOUD's translation, pcd_aug.py:195-196) raise."""
 
     def __init__(self, main_key=None, req_keys=None, rot_range=[-0.78539816, 0.78539816], rot_axis="z",
                  scale_ratio_range=[0.95, 1.05], translation_range=[0, 0, 0], shift_height=False):
         main_key = main_key[0] if isinstance(main_key, (list, tuple)) else main_key
         super().__init__(main_key, req_keys)
-        if scale_ratio_range is not None or translation_range is not None:
-            raise NotImplementedError("GlobalRotScaleTrans: only the rotation-only form (pn_rot.py) is supported")
-        if rot_axis not in ("z", 2):
-            raise NotImplementedError("GlobalRotScaleTrans: only rot_axis='z'")
-        if not isinstance(rot_range, (list, tuple)):
-            rot_range = [-rot_range, rot_range]
-        self.rot_range = [float(rot_range[0]), float(rot_range[1])]
+        if scale_ratio_range is not None:
+            raise NotImplementedError("GlobalRotScaleTrans: scaling is not supported")
+        if (rot_range is None) == (translation_range is None):
+            raise NotImplementedError("GlobalRotScaleTrans: exactly one of rot_range / translation_range (pn_rot.py, pn_shift.py)")
+        if rot_range is not None:
+            self.kind = "rot"
+            if rot_axis not in ("z", 2):
+                raise NotImplementedError("GlobalRotScaleTrans: only rot_axis='z'")
+            if not isinstance(rot_range, (list, tuple)):
+                rot_range = [-rot_range, rot_range]
+            self.rot_range = [float(rot_range[0]), float(rot_range[1])]
+        else:
+            self.kind = "shift"
+            if not shift_height:
+                raise NotImplementedError("GlobalRotScaleTrans: shift_height=False (zeroes the last cloud's shift) is not supported")
+            t = [float(v) for v in translation_range]
+            mags = sorted({v for v in t if v != 0.0})
+            if len(t) != 3 or len(mags) != 1 or mags[0] < 0:
+                raise NotImplementedError("GlobalRotScaleTrans: the shifted axes must share one positive range")
+            self.shift = mags[0]
+            self.axes = sum(1 << i for i, v in enumerate(t) if v != 0.0)
 
     def params(self):
-        return self.kind, self.rot_range[0], self.rot_range[1]
+        if self.kind == "rot":
+            return self.kind, self.rot_range[0], self.rot_range[1]
+        return self.kind, -self.shift, self.shift, self.axes
 
     def __call__(self, data):
         data = dict(data)
-        ang = None
+        draw = None
         for key in self.req_keys:
             if key in data:
                 x = data[key]
-                if ang is None:
-                    ang = torch.empty(x.shape[0], device=x.device).uniform_(*self.rot_range)
-                c, s = torch.cos(ang)[:, None], torch.sin(ang)[:, None]
-                data[key] = torch.stack([c * x[:, 0] - s * x[:, 1], s * x[:, 0] + c * x[:, 1], x[:, 2]], dim=1)
+                if self.kind == "rot":
+                    if draw is None:
+                        draw = torch.empty(x.shape[0], device=x.device).uniform_(*self.rot_range)
+                    c, s = torch.cos(draw)[:, None], torch.sin(draw)[:, None]
+                    data[key] = torch.stack([c * x[:, 0] - s * x[:, 1], s * x[:, 0] + c * x[:, 1], x[:, 2]], dim=1)
+                else:
+                    if draw is None:
+                        draw = (torch.rand(x.shape[0], 3, device=x.device) - 0.5) * 2 * self.shift
+                        draw = draw * torch.tensor([float(bool(self.axes & (1 << i))) for i in range(3)], device=x.device)
+                    data[key] = x + draw[:, :, None]
         return data
 
     def __repr__(self):
-        return f"GlobalRotScaleTrans(rot_range={self.rot_range})"
+        if self.kind == "rot":
+            return f"GlobalRotScaleTrans(rot_range={self.rot_range})"
+        return f"GlobalRotScaleTrans(translation={self.shift}, axes={self.axes:03b})"
 
 
 class DataAugmentations:

@@ -82,3 +82,8 @@ def experiment(algo, suite, obs_aug=None, env_name=None):
 JITTER = dict(type="RandomJitterPoints", main_key="xyz", req_keys=["xyz"], jitter_range=[-0.01, 0.01])
 ROT_Z = dict(type="GlobalRotScaleTrans", main_key="xyz", req_keys=["xyz"], rot_range=[-0.15, 0.15],
              scale_ratio_range=None, translation_range=None, shift_height=False)
+
+
+def shift(translation_range):
+    return dict(type="GlobalRotScaleTrans", main_key="xyz", req_keys=["xyz"], rot_range=None, scale_ratio_range=None,
+                translation_range=list(translation_range), shift_height=True)

@@ -17,7 +17,7 @@ __device__ __forceinline__ int xh_tile_offset(int p, int ch) {
 template <int CP>
 __global__ void __launch_bounds__(256) stage_points_kernel(
     const float* __restrict__ xyz, const void* __restrict__ rgb, int rgb_is_u8, const uint8_t* __restrict__ pos,
-    int n_pos, const uint8_t* __restrict__ seg, int n_seg, int B, int N, int NP, int repeat, int aug_kind, float lo,
+    int n_pos, const uint8_t* __restrict__ seg, int n_seg, int B, int N, int NP, int repeat, int aug_kind, int axis_mask, float lo,
     float hi, const float* __restrict__ noise, uint64_t seed, const uint64_t* __restrict__ counter_dev,
     uint32_t stream_id, float* __restrict__ xf, __nv_bfloat16* __restrict__ xh) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -97,6 +97,22 @@ __global__ void __launch_bounds__(256) stage_points_kernel(
       float xr = c * x0 - s * y0, yr = s * x0 + c * y0;
       x = xr;
       y = yr;
+    } else if (real && aug_kind == PCRL_AUG_SHIFT) {
+      float t0, t1, t2;
+      if (noise) {  // [R, 3] per-cloud translation
+        t0 = noise[(int64_t)r * 3];
+        t1 = noise[(int64_t)r * 3 + 1];
+        t2 = noise[(int64_t)r * 3 + 2];
+      } else {
+        uint4 rnd = philox4x32_10(make_uint4(0xFFFFFFFEu, (uint32_t)r, (uint32_t)cnt, (uint32_t)(cnt >> 32) ^ (stream_id << 24)),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        t0 = (axis_mask & 1) ? lo + (hi - lo) * u01(rnd.x) : 0.f;
+        t1 = (axis_mask & 2) ? lo + (hi - lo) * u01(rnd.y) : 0.f;
+        t2 = (axis_mask & 4) ? lo + (hi - lo) * u01(rnd.z) : 0.f;
+      }
+      x += t0;
+      y += t1;
+      z += t2;
     }
     f[0] = x;
     f[1] = y;
@@ -142,7 +158,11 @@ extern "C" int pcrl_stage_points(const float* xyz, const void* rgb, int rgb_is_u
                                  float aug_hi, const float* noise, uint64_t seed, const uint64_t* counter_dev,
                                  uint32_t stream_id, float* xf, void* xh, int CP, void* stream) {
   PCRL_CHECK_ARG(xyz && xf && B >= 0 && N > 0 && repeat >= 1);
-  PCRL_CHECK_ARG(aug_kind == PCRL_AUG_NONE || aug_kind == PCRL_AUG_JITTER || aug_kind == PCRL_AUG_ROTZ);
+  int axis_mask = (aug_kind >> 8) & 7;
+  aug_kind &= 0xff;
+  if (axis_mask == 0) axis_mask = 7;
+  PCRL_CHECK_ARG(aug_kind == PCRL_AUG_NONE || aug_kind == PCRL_AUG_JITTER || aug_kind == PCRL_AUG_ROTZ ||
+                 aug_kind == PCRL_AUG_SHIFT);
   const int C = 3 + (rgb ? 3 : 0) + (pos ? n_pos : 0) + (seg ? n_seg : 0);
   PCRL_CHECK_ARG((CP == 8 || CP == 16) && C <= CP);
   PCRL_CHECK_ARG(!xh || C + 4 <= 16);
@@ -155,11 +175,11 @@ extern "C" int pcrl_stage_points(const float* xyz, const void* rgb, int rgb_is_u
   cudaStream_t st = as_stream(stream);
   if (CP == 8)
     stage_points_kernel<8><<<blocks, 256, 0, st>>>(xyz, rgb, rgb_is_u8, pos, n_pos, seg, n_seg, B, N, NP, repeat,
-                                                   aug_kind, aug_lo, aug_hi, noise, seed, counter_dev, stream_id, xf,
+                                                   aug_kind, axis_mask, aug_lo, aug_hi, noise, seed, counter_dev, stream_id, xf,
                                                    reinterpret_cast<__nv_bfloat16*>(xh));
   else
     stage_points_kernel<16><<<blocks, 256, 0, st>>>(xyz, rgb, rgb_is_u8, pos, n_pos, seg, n_seg, B, N, NP, repeat,
-                                                    aug_kind, aug_lo, aug_hi, noise, seed, counter_dev, stream_id, xf,
+                                                    aug_kind, axis_mask, aug_lo, aug_hi, noise, seed, counter_dev, stream_id, xf,
                                                     reinterpret_cast<__nv_bfloat16*>(xh));
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;

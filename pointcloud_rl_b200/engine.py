@@ -22,7 +22,7 @@ S_NAMES = [
     "entropy", "actor_grad_sq", "alpha", "alpha_grad",
 ]
 NUM_SCALARS = 16
-AUG_KINDS = {None: 0, "none": 0, "jitter": 1, "rot": 2}
+AUG_KINDS = {None: 0, "none": 0, "jitter": 1, "rot": 2, "shift": 3}
 MLP_KEYS = ["w0", "b0", "w1", "b1", "w2", "b2"]
 PN_KEYS = ["pn.w0", "pn.b0", "pn.w1", "pn.g1", "pn.be1", "pn.w2", "pn.g2", "pn.be2", "pn.wf", "pn.bf", "pn.gf", "pn.bef"]
 
@@ -94,6 +94,7 @@ class HyperParams:
     aug: Optional[str] = None
     aug_lo: float = 0.0
     aug_hi: float = 0.0
+    aug_axes: int = 7  # shift only: bit i set = axis i is translated (include/pcrl.h, PCRL_AUG_SHIFT_AXES)
     tau: float = 0.01
     actor_update_interval: int = 2
     target_update_interval: int = 2
@@ -425,7 +426,7 @@ class UpdateEngine:
 
     def update(self, updates: int, noise: Optional[Dict[str, torch.Tensor]] = None):
         """Enqueues one full update on the current stream.  `noise` (parity mode) injects the reference's
-        random draws: jitter_obs/jitter_next or angle_obs/angle_next, eps_next, eps_pi (device tensors)."""
+        random draws: jitter_obs/jitter_next, angle_obs/angle_next or shift_obs/shift_next, eps_next, eps_pi (device tensors)."""
         sp, hp, w, p, L = self.spec, self.hp, self.w, self.p, self.L
         ST = stream_ptr  # evaluated at every call site: forked sections run on their own stream
         B, R, k = self.B, self.R, self.k
@@ -433,7 +434,9 @@ class UpdateEngine:
         c1, c2, c3 = sp.widths
         noise = noise or {}
         aug = AUG_KINDS[hp.aug] if hp.algo == "drq" else 0
-        nkey = {1: "jitter", 2: "angle"}.get(aug)
+        nkey = {1: "jitter", 2: "angle", 3: "shift"}.get(aug)
+        if aug == 3:
+            aug |= (int(hp.aug_axes) & 7) << 8
         do_actor = updates % hp.actor_update_interval == 0
         do_target = updates % hp.target_update_interval == 0
         ld_cat = D + S + A

@@ -202,7 +202,9 @@ class KernelRunner:
         pos = obs.get("pos_encoding")
         seg = obs.get("seg")
         as_u8 = lambda t: None if t is None else t.contiguous().to(torch.uint8)
-        kind, lo, hi = (0, 0.0, 0.0) if aug is None else aug
+        kind, lo, hi, *rest = (0, 0.0, 0.0) if aug is None else aug
+        if rest and kind == 3:
+            kind |= (int(rest[0]) & 7) << 8
         if self._counter is None:
             self._counter = torch.zeros(1, dtype=torch.int64, device=device)
         L.stage_points(xyz, rgb, int(rgb_u8), as_u8(pos), 0 if pos is None else pos.shape[1], as_u8(seg),

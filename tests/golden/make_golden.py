@@ -44,8 +44,8 @@ def obs_shape_of(obs):
 
 def draw_noise(seed, algo, aug, k, B, N, A, with_actor, rng):
     """Re-draw, with the same seed and in the same order, what the reference draws from the global
-    CPU RNG inside update_parameters: jitter(obs), jitter(next_obs) (pcd_aug.py:318) or the rotation
-    angles (pcd_aug.py:186), eps for a' (distributions.py:117), eps for pi."""
+    CPU RNG inside update_parameters: jitter(obs), jitter(next_obs) (pcd_aug.py:318), the rotation
+    angles (pcd_aug.py:186) or the per-cloud translations (pcd_aug.py:193), eps for a' (distributions.py:117), eps for pi."""
     from torch.distributions.utils import _standard_normal
 
     torch.manual_seed(seed)
@@ -56,6 +56,8 @@ def draw_noise(seed, algo, aug, k, B, N, A, with_actor, rng):
                 noise[f"jitter_{which}"] = torch.FloatTensor(B * k, 3, N).uniform_(*rng)
             elif aug == "rot":
                 noise[f"angle_{which}"] = torch.zeros([B * k, 1]).uniform_(*rng)
+            elif aug == "shift":  # pcd_aug.py:193, translation_range = [hi, hi, hi]
+                noise[f"shift_{which}"] = (torch.rand([B * k, 3]) - 0.5) * 2 * torch.tensor([rng[1]] * 3, dtype=torch.float)
     noise["eps_next"] = _standard_normal((B * k, A), dtype=torch.float32, device=torch.device("cpu"))
     if with_actor:
         noise["eps_pi"] = _standard_normal((B, A), dtype=torch.float32, device=torch.device("cpu"))
@@ -147,6 +149,10 @@ def gen_pointnet_fixture(ns, name, C_extra, B, N, dup, widths=(128, 128, 256), D
 def main():
     ns = load_reference()
     torch.set_num_threads(8)
+    if "--only-shift" in sys.argv:  # added after the other fixtures were committed; they are not regenerated
+        gen_update_fixture(ns, "drq_shift_small", "configs/mfrl/drq/maniskill/pn_shift.py", "drq", "shift", (-0.1, 0.1),
+                           B=5, N=72, A=4, n_seg=1, n_pos=0, S=9, dup=False)
+        return
     gen_pointnet_fixture(ns, "pointnet_fwd_c7", (1, 0), B=3, N=1200, dup=False)
     gen_pointnet_fixture(ns, "pointnet_fwd_c7_dup", (1, 0), B=3, N=1200, dup=True)
     gen_pointnet_fixture(ns, "pointnet_fwd_c9_dmc", (0, 3), B=2, N=1023, dup=False, widths=(64, 128, 256), D=50)
@@ -156,6 +162,8 @@ def main():
                        B=6, N=96, A=5, n_seg=1, n_pos=0, S=13, dup=True)
     gen_update_fixture(ns, "drq_rot_small", "configs/mfrl/drq/maniskill/pn_rot.py", "drq", "rot", (-0.15, 0.15),
                        B=4, N=80, A=5, n_seg=3, n_pos=0, S=13, dup=False)
+    gen_update_fixture(ns, "drq_shift_small", "configs/mfrl/drq/maniskill/pn_shift.py", "drq", "shift", (-0.1, 0.1),
+                       B=5, N=72, A=4, n_seg=1, n_pos=0, S=9, dup=False)
 
 
 if __name__ == "__main__":

@@ -60,9 +60,15 @@ def test_unsupported_options_raise():
         build_all(dict(type="PointNet", feat_dim=6, mlp_spec=[64, 128, 256], out_channels=50, feature_transform=[1]))
     from pointcloud_rl_b200.augmentations import build_data_augmentations
 
-    with pytest.raises(NotImplementedError):
-        build_data_augmentations(dict(type="GlobalRotScaleTrans", main_key="xyz", req_keys=["xyz"], rot_range=None,
-                                      scale_ratio_range=None, translation_range=[0.1, 0.1, 0.1], shift_height=True))
+    shift = dict(type="GlobalRotScaleTrans", main_key="xyz", req_keys=["xyz"], rot_range=None, scale_ratio_range=None,
+                 translation_range=[0.04, 0, 0.04], shift_height=True)
+    assert build_data_augmentations(shift)[0].params() == ("shift", -0.04, 0.04, 0b101)  # pn_shift.py is supported
+    for bad in (dict(shift, shift_height=False),                 # the reference zeroes the last cloud's shift there
+                dict(shift, translation_range=[0.1, 0.2, 0.1]),  # unequal per-axis ranges
+                dict(shift, scale_ratio_range=[0.95, 1.05]),
+                dict(shift, rot_range=[-0.1, 0.1])):
+        with pytest.raises(NotImplementedError):
+            build_data_augmentations(bad)
 
 
 def test_update_needs_cuda_no_cpu_fallback():

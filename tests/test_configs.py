@@ -8,7 +8,8 @@ from pointcloud_rl_b200 import Config, config_path, get_kwargs_from_shape, repla
 from pointcloud_rl_b200.meta import ConfigDict, Registry, build_from_cfg, merge_dicts
 
 FILES = ["mfrl/sac/dm_control/pn.py", "mfrl/sac/maniskill/pn.py", "mfrl/drq/maniskill/pn_jitter.py",
-         "mfrl/drq/maniskill/pn_rot.py", "mfrl/drq/dm_control/pn_jitter.py", "mfrl/drq/dm_control/pn_rot.py"]
+         "mfrl/drq/maniskill/pn_rot.py", "mfrl/drq/dm_control/pn_jitter.py", "mfrl/drq/dm_control/pn_rot.py",
+         "mfrl/drq/maniskill/pn_shift.py", "mfrl/drq/dm_control/pn_shift.py"]
 
 
 def _plain(x):

@@ -114,12 +114,12 @@ def test_tanh_gaussian_fwd_bwd(L):
 
 
 # ------------------------------------------------------------------------------------------ staging
-@pytest.mark.parametrize("aug", ["none", "jitter", "rot"])
+@pytest.mark.parametrize("aug", ["none", "jitter", "rot", "shift"])
 def test_stage_points(L, aug):
     rs = np.random.RandomState(3)
     B, N, k = 5, 200, 2
     obs = O.synthetic_obs(rs, B, N, n_seg=2, n_pos=0)
-    kind = {"none": 0, "jitter": 1, "rot": 2}[aug]
+    kind = {"none": 0, "jitter": 1, "rot": 2, "shift": 3}[aug]
     rep = k if kind else 1
     t = {key: torch.from_numpy(v) for key, v in obs.items()}
     rept = O._repeat_obs(t, rep)
@@ -130,6 +130,9 @@ def test_stage_points(L, aug):
     elif aug == "rot":
         noise = torch.from_numpy(rs.uniform(-0.15, 0.15, size=(B * rep, 1)).astype(np.float32))
         rept["xyz"] = O.aug_rot_z(rept["xyz"], noise)
+    elif aug == "shift":
+        noise = torch.from_numpy(rs.uniform(-0.1, 0.1, size=(B * rep, 3)).astype(np.float32))
+        rept["xyz"] = O.aug_shift(rept["xyz"], noise)
     x_ref = O.preprocess(rept)  # [R, C, N]
     C, NP, CP = x_ref.shape[1], 256, 8
     xf = torch.full((B * rep, NP, CP), 7.0, device="cuda")
@@ -191,6 +194,22 @@ def _run_pointnet_f32(L, p, obs, want_argmax=True):
     L.pointnet_fwd_f32(xf, R, N, NP, CP, C, d["pn.w0"], d["pn.b0"], d["pn.w1"], d["pn.g1"], d["pn.be1"], d["pn.w2"],
                        d["pn.g2"], d["pn.be2"], c1, c2, c3, 1e-6, pooled, argmax, ws, nbytes, sp())
     return x, xf, d, pooled, argmax, (R, N, NP, CP, C, c1, c2, c3)
+
+
+def test_stage_points_philox_shift_axes(L):
+    """Device-side draw of the pn_shift translation: one offset per (cloud, augmentation), uniform in [-t, t], only on
+    the axes the mask enables (dm_control/pn_shift.py shifts x and z)."""
+    B, N, k, t = 64, 130, 2, 0.04
+    xyz = torch.zeros(B, 3, N, device="cuda")
+    xf = torch.zeros(B * k, 256, 8, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    L.stage_points(xyz, None, 0, None, 0, None, 0, B, N, k, 3 | (0b101 << 8), -t, t, None, 7, cnt, 0, xf, None, 8, sp())
+    d = xf[:, :N, :3].cpu()
+    assert torch.equal(d, d[:, :1].expand(-1, N, -1))          # one translation per cloud
+    assert float(d[..., 1].abs().max()) == 0.0                  # y is not shifted
+    sh = d[:, 0, [0, 2]]
+    assert float(sh.abs().max()) <= t and float(sh.std()) > 0.4 * t / 3**0.5 and abs(float(sh.mean())) < 0.2 * t
+    assert len(torch.unique(sh[:, 0])) > B                      # the two augmentations of a sample differ
 
 
 @pytest.mark.parametrize("name", ["pointnet_fwd_c7", "pointnet_fwd_c7_dup", "pointnet_fwd_c9_dmc"])
@@ -374,7 +393,7 @@ def _engine_from_golden(g, precision="fp32"):
     return eng, m
 
 
-@pytest.mark.parametrize("name", ["sac_dmc_small", "drq_jitter_small", "drq_rot_small"])
+@pytest.mark.parametrize("name", ["sac_dmc_small", "drq_jitter_small", "drq_rot_small", "drq_shift_small"])
 def test_update_matches_reference_fp32(name):
     g = load_golden(name)
     eng, m = _engine_from_golden(g)
