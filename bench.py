@@ -272,7 +272,7 @@ def native_arm(args, w, rank, world, local_rank):
     host_batches = [synthetic_batch(100 * rank + i, w["B"], w["N"], w["A"], n_seg=w["n_seg"], n_pos=w["n_pos"],
                                     state_dim=w["S"]) for i in range(n_pool)]
     pinned = [eng.make_pinned_batch(b) for b in host_batches]
-    resident = [{k: v.to(device) for k, v in pb.items()} for pb in pinned]
+    resident = [eng.to_device_batch(pb) for pb in pinned]
     step_fn = eng.update_graphed if not args.no_graph else eng.update
 
     def barrier():
@@ -325,10 +325,10 @@ def native_arm(args, w, rank, world, local_rank):
     d2h_bytes = 0
     for i in range(args.steps):
         eng.adopt(i % 2, ev)
-        copy_stream.wait_stream(torch.cuda.current_stream())  # landing slot reuse is ordered after the adopt
-        if i + 1 < args.steps:
-            ev, _ = eng.h2d_async(pinned[(i + 1) % n_pool], (i + 1) % 2, copy_stream)  # overlaps update i
         step_fn(i + 1)
+        if i + 1 < args.steps:
+            # the other landing slot was last read by the adopt of step i-1, which has completed (per-step sync below)
+            ev, _ = eng.h2d_async(pinned[(i + 1) % n_pool], (i + 1) % 2, copy_stream)  # overlaps update i
         ret = eng.read_scalars(i + 1, sync=True)  # the loss/metrics every update_parameters call returns
         d2h_bytes = eng.scalars.numel() * 4
     e3.record()
@@ -382,7 +382,8 @@ def native_arm(args, w, rank, world, local_rank):
     line = {
         "metric": "update_encoded_points_per_s", "value": pts / (ms_step * 1e-3), "unit": "points/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "steps_per_s": 1e3 / ms_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": args.workload, "batch_per_gpu": w["B"], "points": w["N"], "channels": spec.C,
                    "num_aug": eng.k, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
                    "l2": "4 distinct resident batches rotated; per-step working set (staged points, activations of the compacted backward, 27 MB weights+Adam state) exceeds the 126 MB L2"},
@@ -417,8 +418,16 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-window", action="store_true", help="run 2 eager updates inside cudaProfilerStart/Stop and exit")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling (SURVEY.md section 8d row 4): split this global minibatch over the ranks "
+                         "(e.g. 256 or 2048); default 0 = weak scaling, the workload's batch on every rank")
     args = ap.parse_args()
-    w = WORKLOADS[args.workload]
+    w = dict(WORKLOADS[args.workload])
+    if args.global_batch:
+        world_ = int(os.environ.get("WORLD_SIZE", 1))
+        if args.global_batch % world_:
+            raise SystemExit("--global-batch must be divisible by the number of ranks")
+        w["B"] = args.global_batch // world_
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))

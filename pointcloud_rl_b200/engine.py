@@ -184,21 +184,34 @@ class UpdateEngine:
         u8 = dict(dtype=torch.uint8, device=dev)
         Kp = (D + S + 3) // 4 * 4
         self.actor_w0p = torch.zeros(h1, Kp, **f32) if (self.tf32 and Kp != D + S and Kp <= D + S + A) else None
-        self.raw = {}
+        # The replay sample lives in ONE contiguous device buffer (leaves are 256-byte aligned views), so a batch
+        # moves host -> landing slot -> here with a single copy each instead of one per leaf.
+        leaves = []
         for which in ("obs", "next_obs"):
-            d = {"xyz": torch.zeros(B, 3, N, **f32)}
+            leaves.append((f"{which}/xyz", (B, 3, N), torch.float32))
             if sp.has_rgb:
-                d["rgb"] = torch.zeros(B, 3, N, **(u8 if sp.rgb_u8 else f32))
+                leaves.append((f"{which}/rgb", (B, 3, N), torch.uint8 if sp.rgb_u8 else torch.float32))
             if sp.n_pos:
-                d["pos_encoding"] = torch.zeros(B, sp.n_pos, N, **u8)
+                leaves.append((f"{which}/pos_encoding", (B, sp.n_pos, N), torch.uint8))
             if sp.n_seg:
-                d["seg"] = torch.zeros(B, sp.n_seg, N, **u8)
+                leaves.append((f"{which}/seg", (B, sp.n_seg, N), torch.uint8))
             if S:
-                d["state"] = torch.zeros(B, S, **f32)
-            self.raw[which] = d
-        self.raw["actions"] = torch.zeros(B, A, **f32)
-        self.raw["rewards"] = torch.zeros(B, **f32)
-        self.raw["dones"] = torch.zeros(B, **u8)
+                leaves.append((f"{which}/state", (B, S), torch.float32))
+        leaves += [("actions", (B, A), torch.float32), ("rewards", (B,), torch.float32), ("dones", (B,), torch.uint8)]
+        self._batch_layout, off = [], 0
+        for key, shape, dt in leaves:
+            nbytes = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+            self._batch_layout.append((key, shape, dt, off, nbytes))
+            off += (nbytes + 255) // 256 * 256
+        self._batch_bytes = off
+        self.raw_flat = torch.zeros(off, **u8)
+        self.raw = {"obs": {}, "next_obs": {}}
+        for key, view in self._batch_views(self.raw_flat).items():
+            if "/" in key:
+                a, b = key.split("/")
+                self.raw[a][b] = view
+            else:
+                self.raw[key] = view
         self._pinned = None
 
         w = {}
@@ -269,17 +282,20 @@ class UpdateEngine:
         """batch: dict(obs, next_obs, actions, rewards, dones) of numpy arrays / torch CPU tensors (the
         reference's `memory.sample(B)` layout, replay_buffer.py:297-322).  Host->device copies go through
         pinned staging buffers so they are asynchronous on the current stream."""
-        flat = self._flatten_batch(batch)
-        nbytes = 0
         if self._pinned is None:
-            self._pinned = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in flat.items()}
-        for key, src in flat.items():
-            dst = self._device_leaf(key)
-            pin = self._pinned[key]
-            pin.copy_(src)
-            dst.copy_(pin, non_blocking=True)
-            nbytes += pin.numel() * pin.element_size()
-        return nbytes
+            self._pinned = torch.empty(self._batch_bytes, dtype=torch.uint8).pin_memory()
+            self._pinned_views = self._batch_views(self._pinned)
+        for key, src in self._flatten_batch(batch).items():
+            self._pinned_views[key].copy_(src)
+        self.raw_flat.copy_(self._pinned, non_blocking=True)
+        return sum(n for *_, n in self._batch_layout)
+
+    def _batch_views(self, flat):
+        """Typed leaf views (flattened keys) into a byte buffer laid out like `raw_flat`."""
+        out = {}
+        for key, shape, dt, off, nbytes in self._batch_layout:
+            out[key] = flat[off:off + nbytes].view(dt).view(shape)
+        return out
 
     def _device_leaf(self, key):
         if "/" in key:
@@ -586,30 +602,40 @@ class UpdateEngine:
 
     # ------------------------------------------------------------------ pipelined host->device input path
     def make_pinned_batch(self, batch):
-        """The replay sample laid out in pinned host memory (what a pinned replay ring would hand over)."""
-        return {k: v.contiguous().pin_memory() for k, v in self._flatten_batch(batch).items()}
+        """The replay sample laid out in pinned host memory (what a pinned replay ring would hand over): one contiguous
+        buffer with the device layout; the returned dict holds its leaf views plus the buffer itself under "_flat"."""
+        flat = torch.empty(self._batch_bytes, dtype=torch.uint8).pin_memory()
+        views = self._batch_views(flat)
+        for k, v in self._flatten_batch(batch).items():
+            views[k].copy_(v)
+        views["_flat"] = flat
+        return views
 
     def h2d_async(self, pinned, slot, copy_stream):
-        """Enqueue the H2D copies of one batch into landing buffer `slot` on `copy_stream`; returns (event, bytes)."""
+        """Enqueue the H2D copy of one batch into landing buffer `slot` on `copy_stream`; returns (event, bytes)."""
         if self._landing is None:
-            self._landing = [{k: torch.empty_like(self._device_leaf(k)) for k in pinned} for _ in range(2)]
-        nbytes = 0
+            self._landing = [torch.empty_like(self.raw_flat) for _ in range(2)]
+        src = pinned["_flat"]
         with torch.cuda.stream(copy_stream):
-            for k, src in pinned.items():
-                self._landing[slot][k].copy_(src, non_blocking=True)
-                nbytes += src.numel() * src.element_size()
+            self._landing[slot].copy_(src, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return ev, nbytes
+        return ev, sum(n for *_, n in self._batch_layout)
 
     def adopt(self, slot, event):
-        """Make landing buffer `slot` the current batch (device-to-device, on the current stream)."""
+        """Make landing buffer `slot` the current batch (one device-to-device copy on the current stream)."""
         torch.cuda.current_stream().wait_event(event)
-        for k, src in self._landing[slot].items():
-            self._device_leaf(k).copy_(src, non_blocking=True)
+        self.raw_flat.copy_(self._landing[slot], non_blocking=True)
+
+    def to_device_batch(self, pinned):
+        """A batch resident in HBM (for set_batch_device)."""
+        return {"_flat": pinned["_flat"].to(self.device)}
 
     def set_batch_device(self, dev_batch):
-        """Batch already resident in HBM (flattened keys as make_pinned_batch): device-to-device adopt."""
+        """Batch already resident in HBM: device-to-device adopt."""
+        if "_flat" in dev_batch:
+            self.raw_flat.copy_(dev_batch["_flat"], non_blocking=True)
+            return
         for k, src in dev_batch.items():
             self._device_leaf(k).copy_(src, non_blocking=True)
 
