@@ -97,6 +97,11 @@ int pcrl_pointnet_pack_weights(const float* w0, const float* b0, const float* w1
 int pcrl_pointnet_fwd_bf16(const void* xh, int R, int N, int NP, const void* wpack, int c1, int c2, int c3,
                            float ln_eps, uint64_t* pool_keys /* [R,c3] scratch */, float* pooled, int32_t* argmax,
                            void* stream);
+/* Same, but output cloud r reads the staged tiles of source cloud r * src_cloud_stride: DrQ's actor step encodes the
+ * first of the num_aug staged copies of every sample (drq.py:115) without gathering them first. */
+int pcrl_pointnet_fwd_bf16_strided(const void* xh, int R, int src_cloud_stride, int N, int NP, const void* wpack, int c1,
+                                   int c2, int c3, float ln_eps, uint64_t* pool_keys, float* pooled, int32_t* argmax,
+                                   void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (3) Sparse backward of (2) through the saved argmax (autograd of pointnet.py:151 + ConvMLP).

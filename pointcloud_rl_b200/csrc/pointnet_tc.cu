@@ -272,7 +272,7 @@ __host__ __device__ inline SmemLayout make_layout(int c1, int c2, int c3) {
 // first half of tile i: the pool group, which is the bottleneck stage, never waits for the tensor pipe.
 __global__ void __launch_bounds__(kThreads, 1)
 pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpack, int n_tiles, int tiles_per_cloud,
-                       int N, int c1, int c2, int c3, float ln_eps, int want_argmax,
+                       int src_cloud_stride, int c1, int c2, int c3, float ln_eps, int want_argmax,
                        unsigned long long* __restrict__ pool_keys, DumpOut dump) {
   extern __shared__ __align__(128) unsigned char smem[];
   const SmemLayout L = make_layout(c1, c2, c3);
@@ -360,7 +360,11 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
         if (i >= kStages) mbar_wait_relaxed(BAR(XE + st), ((i / kStages) - 1) & 1, 100);
         mbar_expect_tx(BAR(XF + st), kTileBytes);
         const int64_t tile = tile0 + i;
-        bulk_g2s(sbase + L.xst + st * kTileBytes, xh + tile * kTileBytes, kTileBytes, BAR(XF + st));
+        // cloud r reads the tiles of source cloud r * src_cloud_stride (the actor step encodes the first of the
+        // num_aug staged copies of every sample in place)
+        const int64_t src_tile = src_cloud_stride == 1 ? tile
+                                                        : (tile / tiles_per_cloud) * src_cloud_stride * tiles_per_cloud + tile % tiles_per_cloud;
+        bulk_g2s(sbase + L.xst + st * kTileBytes, xh + src_tile * kTileBytes, kTileBytes, BAR(XF + st));
       }
     }
   } else if (warp == 1) {
@@ -835,7 +839,7 @@ int recompute_active_tc(const void* xh, const void* wpack, const int32_t* src, c
   const int n_tiles = (int)cdiv(capacity, 128);
   DumpOut d{count_dev, h0, xhat1, rstd1, h1, xhat2, rstd2, m1, m2};
   pointnet_fwd_tc_kernel<<<std::min(sm_count(), n_tiles), kThreads, L.total, st>>>(
-      (const char*)xha_scratch, (const char*)wpack, n_tiles, /*tiles_per_cloud=*/1 << 30, /*N=*/0, c1, c2, c3, ln_eps, 0,
+      (const char*)xha_scratch, (const char*)wpack, n_tiles, /*tiles_per_cloud=*/1 << 30, /*src_cloud_stride=*/1, c1, c2, c3, ln_eps, 0,
       nullptr, d);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
@@ -882,7 +886,13 @@ int pcrl_pointnet_pack_weights(const float* w0, const float* b0, const float* w1
 
 int pcrl_pointnet_fwd_bf16(const void* xh, int R, int N, int NP, const void* wpack, int c1, int c2, int c3,
                            float ln_eps, uint64_t* pool_keys, float* pooled, int32_t* argmax, void* stream) {
-  PCRL_CHECK_ARG(xh && wpack && pool_keys && pooled && R >= 0 && N > 0 && NP >= N && NP % 128 == 0);
+  return pcrl_pointnet_fwd_bf16_strided(xh, R, 1, N, NP, wpack, c1, c2, c3, ln_eps, pool_keys, pooled, argmax, stream);
+}
+
+int pcrl_pointnet_fwd_bf16_strided(const void* xh, int R, int src_cloud_stride, int N, int NP, const void* wpack, int c1,
+                                   int c2, int c3, float ln_eps, uint64_t* pool_keys, float* pooled, int32_t* argmax,
+                                   void* stream) {
+  PCRL_CHECK_ARG(xh && wpack && pool_keys && pooled && R >= 0 && N > 0 && NP >= N && NP % 128 == 0 && src_cloud_stride >= 1);
   if (!tc::shapes_ok(c1, c2, c3)) {
     set_error("pcrl_pointnet_fwd_bf16: widths (%d,%d,%d) unsupported (multiples of 64/64/128 up to 256, max(c1,c2) + 1.5*c3 <= 512, smem budget)", c1,
               c2, c3);
@@ -902,7 +912,7 @@ int pcrl_pointnet_fwd_bf16(const void* xh, int R, int N, int NP, const void* wpa
   PCRL_CHECK_CUDA(cudaMemsetAsync(pool_keys, 0, (int64_t)R * c3 * sizeof(uint64_t), st));
   const int grid = std::min(sm_count(), n_tiles);
   tc::pointnet_fwd_tc_kernel<<<grid, tc::kThreads, L.total, st>>>((const char*)xh, (const char*)wpack, n_tiles,
-                                                                  tiles_per_cloud, N, c1, c2, c3, ln_eps,
+                                                                  tiles_per_cloud, src_cloud_stride, c1, c2, c3, ln_eps,
                                                                   argmax != nullptr,
                                                                   (unsigned long long*)pool_keys, tc::DumpOut{});
   PCRL_CHECK_LAUNCH();

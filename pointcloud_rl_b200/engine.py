@@ -256,7 +256,7 @@ class UpdateEngine:
         self.w = w
         self._graphs = {}
         self.graph_calls = {}
-        self._side = [torch.cuda.Stream(device=dev) for _ in range(5)] if dev.type == "cuda" else []
+        self._side = [torch.cuda.Stream(device=dev) for _ in range(9)] if dev.type == "cuda" else []
         self._landing = None
 
     # ------------------------------------------------------------------ parameters
@@ -336,8 +336,12 @@ class UpdateEngine:
         c1, c2, c3 = sp.widths
         argmax = w["argmax_obs"] if want_argmax else None
         if self.precision == "bf16":
-            self.L.pointnet_fwd_bf16(w[f"xh_{name}"], rows, sp.n_points, sp.NP, w["wpack"], c1, c2, c3, sp.ln_eps,
-                                     w[f"pool_keys_{name}"], w[f"pooled_{name}"], argmax, st)
+            if name == "pi" and self.k > 1:  # first augmentation of every sample, read in place from the obs staging
+                self.L.pointnet_fwd_bf16_strided(w["xh_obs"], rows, self.k, sp.n_points, sp.NP, w["wpack"], c1, c2, c3,
+                                                 sp.ln_eps, w["pool_keys_pi"], w["pooled_pi"], argmax, st)
+            else:
+                self.L.pointnet_fwd_bf16(w[f"xh_{name}"], rows, sp.n_points, sp.NP, w["wpack"], c1, c2, c3, sp.ln_eps,
+                                         w[f"pool_keys_{name}"], w[f"pooled_{name}"], argmax, st)
         else:
             self.L.pointnet_fwd_f32(w[f"xf_{name}"], rows, sp.n_points, sp.NP, sp.CP, sp.C, p["pn.w0"], p["pn.b0"],
                                     p["pn.w1"], p["pn.g1"], p["pn.be1"], p["pn.w2"], p["pn.g2"], p["pn.be2"], c1, c2,
@@ -376,18 +380,20 @@ class UpdateEngine:
     def _mlp_bwd(self, net, x, K, M, dout, lddo, nout, keep, dx, want_w, st, scratch="a", wstream=None):
         """Backward of one 3-layer head.  The data-gradient chain (dX of layer 3 -> 2 -> 1) is the critical path; the
         weight/bias gradients only feed the optimizer, so with `wstream` (a side-stream index) they are enqueued on
-        a forked stream, layer by layer behind the dY they need, and joined at the end."""
+        forked streams (`wstream`: three side-stream indices), each behind the dY it needs, and joined at the end."""
         p, g, (h1n, h2n) = self.p, self.g, self.spec.hidden
         h1, h2 = self.w[f"h1_{keep}"], self.w[f"h2_{keep}"]
         w = {"dh1": self.w[f"dh1_{scratch}"], "dh2": self.w[f"dh2_{scratch}"]}
         L = self.L
-        side = self._side[wstream] if (want_w and wstream is not None) else None
+        sides = [self._side[i] for i in wstream] if (want_w and wstream is not None) else None
         main = torch.cuda.current_stream()
 
         def wgrad(xin, ldx, name, dy, lddy, Kin, Nout_):
-            """dW/db of one layer (dy is complete on the main stream when this is called)."""
+            """dW/db of one layer (dy is complete on the main stream when this is called); every layer has its own
+            side stream, so the three weight-gradient GEMMs of a head also overlap each other."""
             if not want_w:
                 return
+            side = sides[name] if sides is not None else None
             if side is None:
                 L.linear_bwd(xin, ldx, p[f"{net}.w{name}"], dy, lddy, g[f"{net}.w{name}"], g[f"{net}.b{name}"], None, 0,
                              None, 0, M, Kin, Nout_, self.tf32, stream_ptr())
@@ -408,8 +414,9 @@ class UpdateEngine:
         if dx is not None:
             L.linear_bwd(x, x.stride(0), p[f"{net}.w0"], w["dh1"], h1n, None, None, dx, dx.stride(0), None, 0, M, K, h1n,
                          self.tf32, stream_ptr())
-        if side is not None:
-            main.wait_stream(side)
+        if sides is not None:
+            for side in sides:
+                main.wait_stream(side)
 
     def _adam(self, group, idx, lr, betas, gradsq_slot, polyak, st):
         lo, hi = self.layout.group_range[group]
@@ -501,8 +508,8 @@ class UpdateEngine:
         # ---- critic backward: the two heads in parallel, their feature gradients add (sac.py:141-142)
         s_q = self._fork(2)
         with torch.cuda.stream(s_q):
-            self._mlp_bwd("q1", cat, ld_cat, R, w["dq"][:, 1:], 2, 1, "q1", w["dx1"], True, ST(), "b", wstream=3)
-        self._mlp_bwd("q0", cat, ld_cat, R, w["dq"], 2, 1, "q0", w["dx0"], True, ST(), "a", wstream=4)
+            self._mlp_bwd("q1", cat, ld_cat, R, w["dq"][:, 1:], 2, 1, "q1", w["dx1"], True, ST(), "b", wstream=(3, 4, 5))
+        self._mlp_bwd("q0", cat, ld_cat, R, w["dq"], 2, 1, "q0", w["dx0"], True, ST(), "a", wstream=(6, 7, 8))
         self._join(s_q)
         q_pending = None
         if self.allreduce is not None:
@@ -529,7 +536,8 @@ class UpdateEngine:
         # ---- actor + alpha step: sac.py:161-205 / drq.py:114-155
         if do_actor:
             if k > 1:  # first augmentation of every sample (drq.py:115)
-                self._take_first_aug(ST())
+                if self.precision != "bf16":
+                    self._take_first_aug(ST())  # the tensor-core path reads the obs staging in place (strided encode)
                 name = "pi"
             else:
                 name = "obs"
@@ -560,7 +568,7 @@ class UpdateEngine:
             L.add_cols(da, ld_cat, w["dx1"][:, D + S:], ld_cat, da, ld_cat, B, A, ST())
             L.tanh_gaussian_bwd_dev(w["out_pi"], w["eps_pi"], da, ld_cat, self.alpha_dev, B, A, hp.log_std_bound[0],
                                     hp.log_std_bound[1], hp.head_scale, w["dout"], ST())
-            self._mlp_bwd("actor", cat, D + S, B, w["dout"], 2 * A, 2 * A, "actor", None, True, ST(), "a", wstream=3)
+            self._mlp_bwd("actor", cat, D + S, B, w["dout"], 2 * A, 2 * A, "actor", None, True, ST(), "a", wstream=(3, 4, 5))
             if self.allreduce is not None:
                 al_lo, al_hi = self.layout.group_range["alpha"]
                 self.allreduce(self.grads[a_lo:al_hi])  # actor grads | d log_alpha in one message
