@@ -56,13 +56,13 @@ int pcrl_sm_count(void);
  *   xyz  f32 [B,3,N];  rgb u8 or f32 [B,3,N] (may be NULL; rgb_is_u8 selects /255);
  *   pos  u8 [B,n_pos,N] (may be NULL);  seg u8/bool [B,n_seg,N] (may be NULL)
  * randomness: if `noise` != NULL it is used verbatim (parity mode): JITTER -> f32 [B*repeat,3,N],
- *   ROTZ -> f32 [B*repeat] angles.  Otherwise Philox4x32-10 keyed by (seed, *counter_dev + stream_id).
+ *   ROTZ -> f32 [B*repeat] angles, SHIFT -> f32 [B*repeat,3] translations.  Otherwise Philox4x32-10 keyed by
+ *   (seed, *counter_dev + stream_id).
  * outputs:
- *   xf   f32  [B*repeat, NP, CP]  point-major rows (xyz | rgb/255 | pos | seg | 0 pad)
+ *   xf   f32  [B*repeat, NP, CP]  point-major rows (xyz | rgb/255 | pos | seg | 0 pad); may be NULL when xh is given
+ *        (the no-grad target branch of the tensor-core path never reads it)
  *   xh   bf16 tile images for the tcgen05 path, [B*repeat*NP/128][128x16] (may be NULL), holding
  *        hi parts of all channels, a constant-1 channel (bias) and the lo parts of xyz
- * row_stride_select: if >1, only source rows are staged for output rows r with r % row_stride_select
- *   == 0 of an already-staged buffer -- not used here; see pcrl_gather_rows.
  * ------------------------------------------------------------------------------------------- */
 int pcrl_stage_points(const float* xyz, const void* rgb, int rgb_is_u8, const uint8_t* pos, int n_pos,
                       const uint8_t* seg, int n_seg, int B, int N, int repeat, int aug_kind, float aug_lo,
@@ -95,7 +95,7 @@ int pcrl_pointnet_pack_weights(const float* w0, const float* b0, const float* w1
                                int rgb_u8 /* xh holds raw 0..255 rgb: fold 1/255 into w0 */, void* wpack,
                                void* stream);
 int pcrl_pointnet_fwd_bf16(const void* xh, int R, int N, int NP, const void* wpack, int c1, int c2, int c3,
-                           float ln_eps, uint64_t* pool_keys /* [R,c3] scratch */, float* pooled, int32_t* argmax,
+                           float ln_eps, uint64_t* pool_keys /* [R,c3] scratch: zero before the first call, every call leaves it zeroed */, float* pooled, int32_t* argmax,
                            void* stream);
 /* Same, but output cloud r reads the staged tiles of source cloud r * src_cloud_stride: DrQ's actor step encodes the
  * first of the num_aug staged copies of every sample (drq.py:115) without gathering them first. */

@@ -722,14 +722,16 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
 
 // pooled[r][c] = relu(|g2[c]| * max_p z + b2[c]) and the argmax, from the packed (key, ~index) maxima stored at the
 // permuted channel position pos[c]
-__global__ void pool_finalize_kernel(const unsigned long long* __restrict__ keys, int R, int c3,
+__global__ void pool_finalize_kernel(unsigned long long* __restrict__ keys, int R, int c3,
                                      const float* __restrict__ g2, const float* __restrict__ be2,
                                      const int* __restrict__ pos, float* __restrict__ pooled,
                                      int32_t* __restrict__ argmax) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)R * c3) return;
   const int r = (int)(i / c3), c = (int)(i % c3);
-  const unsigned long long k = keys[(int64_t)r * c3 + pos[c]];
+  unsigned long long* kp = keys + (int64_t)r * c3 + pos[c];
+  const unsigned long long k = *kp;
+  *kp = 0ull;  // leave the scratch zeroed for the next call (pos is a permutation: every key is read exactly once)
   const float z = __uint_as_float((uint32_t)(k >> 32)) - kKeyBias;
   pooled[i] = fmaxf(fmaf(fabsf(g2[c]), z, be2[c]), 0.f);
   if (argmax) argmax[i] = (int32_t)(0xFFFFFFFFu - (uint32_t)k);
@@ -909,7 +911,6 @@ int pcrl_pointnet_fwd_bf16_strided(const void* xh, int R, int src_cloud_stride, 
   }
   const int tiles_per_cloud = NP / 128;
   const int n_tiles = R * tiles_per_cloud;
-  PCRL_CHECK_CUDA(cudaMemsetAsync(pool_keys, 0, (int64_t)R * c3 * sizeof(uint64_t), st));
   const int grid = std::min(sm_count(), n_tiles);
   tc::pointnet_fwd_tc_kernel<<<grid, tc::kThreads, L.total, st>>>((const char*)xh, (const char*)wpack, n_tiles,
                                                                   tiles_per_cloud, src_cloud_stride, c1, c2, c3, ln_eps,
@@ -920,7 +921,7 @@ int pcrl_pointnet_fwd_bf16_strided(const void* xh, int R, int src_cloud_stride, 
   const tc::WpackLayout W = tc::make_wpack(c1, c2, c3);
   const float* prm = reinterpret_cast<const float*>((const char*)wpack + W.prm);
   tc::pool_finalize_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(
-      (const unsigned long long*)pool_keys, R, c3, prm + 2 * c2, prm + 2 * c2 + c3,
+      (unsigned long long*)pool_keys, R, c3, prm + 2 * c2, prm + 2 * c2 + c3,
       reinterpret_cast<const int*>((const char*)wpack + W.pos), pooled, argmax);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;

@@ -117,9 +117,11 @@ __global__ void __launch_bounds__(256) stage_points_kernel(
     f[0] = x;
     f[1] = y;
     f[2] = z;
-    float4* dst = reinterpret_cast<float4*>(xf + ((int64_t)r * NP + n_out) * CP);
+    if (xf) {
+      float4* dst = reinterpret_cast<float4*>(xf + ((int64_t)r * NP + n_out) * CP);
 #pragma unroll
-    for (int q = 0; q < CP / 4; ++q) dst[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+      for (int q = 0; q < CP / 4; ++q) dst[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+    }
 
     if (xh) {
       // bf16 operand row for the layer-0 MMA (K=16): channels [0,C) hi parts (u8 rgb kept as the
@@ -157,7 +159,7 @@ extern "C" int pcrl_stage_points(const float* xyz, const void* rgb, int rgb_is_u
                                  const uint8_t* seg, int n_seg, int B, int N, int repeat, int aug_kind, float aug_lo,
                                  float aug_hi, const float* noise, uint64_t seed, const uint64_t* counter_dev,
                                  uint32_t stream_id, float* xf, void* xh, int CP, void* stream) {
-  PCRL_CHECK_ARG(xyz && xf && B >= 0 && N > 0 && repeat >= 1);
+  PCRL_CHECK_ARG(xyz && (xf || xh) && B >= 0 && N > 0 && repeat >= 1);
   int axis_mask = (aug_kind >> 8) & 7;
   aug_kind &= 0xff;
   if (axis_mask == 0) axis_mask = 7;

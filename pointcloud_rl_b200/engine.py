@@ -217,7 +217,8 @@ class UpdateEngine:
         w = {}
         bf16 = self.precision == "bf16"
         for name, rows in (("next", R), ("obs", R), ("pi", B)):
-            w[f"xf_{name}"] = torch.zeros(rows, NP, CP, **f32)
+            if not bf16 or name == "obs":  # tensor-core path: only the critic's backward reads the fp32 staging
+                w[f"xf_{name}"] = torch.zeros(rows, NP, CP, **f32)
             if bf16:
                 w[f"xh_{name}"] = torch.zeros(rows * NP * 16, dtype=torch.bfloat16, device=dev)
             w[f"pooled_{name}"] = torch.zeros(rows, c3, **f32)
@@ -327,7 +328,7 @@ class UpdateEngine:
         self.L.stage_points(
             raw["xyz"], raw.get("rgb"), int(sp.rgb_u8), raw.get("pos_encoding"), sp.n_pos, raw.get("seg"), sp.n_seg,
             self.B, sp.n_points, repeat, aug_kind, float(self.hp.aug_lo), float(self.hp.aug_hi), noise, self.seed,
-            self.counter, stream_id, self.w[f"xf_{name}"], self.w.get(f"xh_{name}"), sp.CP, st)
+            self.counter, stream_id, self.w.get(f"xf_{name}"), self.w.get(f"xh_{name}"), sp.CP, st)
 
     def _encode(self, name, rows, want_argmax, st):
         """PointNet per-point MLP + max-pool (pointnet.py:147-151) then final_mlp (pointnet.py:110,152-153):
