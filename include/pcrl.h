@@ -69,6 +69,13 @@ int pcrl_stage_points(const float* xyz, const void* rgb, int rgb_is_u8, const ui
                       float aug_hi, const float* noise, uint64_t seed, const uint64_t* counter_dev,
                       uint32_t stream_id, float* xf, void* xh, int CP, void* stream);
 
+/* Device-resident replay sampling (replaces ReplayMemory.sample's numpy `take` per key + the per-leaf H2D copies,
+ * replay_buffer.py:297-322, dict_array.py:308-318): for every leaf l of a transition, dst_l[b] = src_l[idx[b]].
+ * src_ptrs / dst_ptrs / row_bytes are DEVICE arrays of n_leaves entries (leaf base addresses and bytes per row),
+ * idx is a device array of B ring positions (drawn on the host by the sampler, sampling_strategy.py:26-31). */
+int pcrl_gather_transitions(const uint64_t* src_ptrs, const uint64_t* dst_ptrs, const int64_t* row_bytes, int n_leaves,
+                            const int64_t* idx, int B, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (2) PointNet per-point shared MLP + max-pool.  Replaces ConvMLP (mlp.py:15-94; block_utils.py),
  * LN1d (nn_layer.py:192-225) and feature.max(-1) (pointnet.py:151):

@@ -273,16 +273,26 @@ class SAC(BaseAgent):
 
     # ------------------------------------------------------------------ the public step
     def _sample(self, memory):
-        batch = unwrap(memory.sample(self.batch_size))
+        batch = memory.sample(self.batch_size)
+        if hasattr(batch, "gather_into"):  # device-resident replay ring (replay.py): stays on the GPU
+            if self.use_episode_dones:
+                raise NotImplementedError("use_episode_dones with the device replay ring")
+            return batch
+        batch = unwrap(batch)
         if self.use_episode_dones:
             batch["dones"] = batch["episode_dones"]
         return batch
 
     def update_parameters(self, memory, updates):
-        """sac.py:103-214 -- same call, same returned dict; one H2D batch copy in, one scalar copy out."""
+        """sac.py:103-214 -- same call, same returned dict; one H2D batch copy in (none with the device replay ring),
+        one scalar copy out."""
         batch = self._sample(memory)
-        eng = self._ensure_engine(batch)
-        eng.upload_batch(batch)
+        if hasattr(batch, "gather_into"):
+            eng = self._ensure_engine(None if self.engine is not None else batch.to_host())
+            batch.gather_into(eng)
+        else:
+            eng = self._ensure_engine(batch)
+            eng.upload_batch(batch)
         if self.use_cuda_graph:
             eng.update_graphed(updates)
         else:

@@ -1,6 +1,7 @@
 // Replay-minibatch staging with the DrQ augmentation fused into the load.
 // One thread per (source cloud, point): the channel-major source is read once (coalesced along the
 // point axis) and `repeat` augmented point-major rows are written.
+#include <algorithm>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -151,9 +152,43 @@ __global__ void __launch_bounds__(256) stage_points_kernel(
   }
 }
 
+// Replay sampling on the device: dst_leaf[b] = src_leaf[idx[b]] for every leaf of a transition, one launch.
+// blockIdx.y = leaf, blockIdx.x = sampled row; rows are copied as 16-byte vectors when both sides allow it.
+__global__ void __launch_bounds__(256) gather_transitions_kernel(const unsigned long long* __restrict__ src_ptrs,
+                                                                 const unsigned long long* __restrict__ dst_ptrs,
+                                                                 const long long* __restrict__ row_bytes,
+                                                                 const long long* __restrict__ idx, int B) {
+  const int leaf = blockIdx.y;
+  const long long nb = row_bytes[leaf];
+  const char* src = reinterpret_cast<const char*>(src_ptrs[leaf]);
+  char* dst = reinterpret_cast<char*>(dst_ptrs[leaf]);
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const char* s = src + idx[b] * nb;
+    char* d = dst + (long long)b * nb;
+    if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d) | (uintptr_t)nb) & 15) == 0) {
+      for (long long o = (long long)threadIdx.x * 16; o < nb; o += 256 * 16)
+        *reinterpret_cast<uint4*>(d + o) = *reinterpret_cast<const uint4*>(s + o);
+    } else {
+      for (long long o = threadIdx.x; o < nb; o += 256) d[o] = s[o];
+    }
+  }
+}
+
 }  // namespace pcrl
 
 using namespace pcrl;
+
+extern "C" int pcrl_gather_transitions(const uint64_t* src_ptrs, const uint64_t* dst_ptrs, const int64_t* row_bytes,
+                                       int n_leaves, const int64_t* idx, int B, void* stream) {
+  PCRL_CHECK_ARG(src_ptrs && dst_ptrs && row_bytes && idx && n_leaves >= 1 && B >= 0);
+  if (B == 0) return PCRL_OK;
+  dim3 grid((unsigned)std::min(B, 4096), (unsigned)n_leaves);
+  gather_transitions_kernel<<<grid, 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const unsigned long long*>(src_ptrs), reinterpret_cast<const unsigned long long*>(dst_ptrs),
+      reinterpret_cast<const long long*>(row_bytes), reinterpret_cast<const long long*>(idx), B);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
 
 extern "C" int pcrl_stage_points(const float* xyz, const void* rgb, int rgb_is_u8, const uint8_t* pos, int n_pos,
                                  const uint8_t* seg, int n_seg, int B, int N, int repeat, int aug_kind, float aug_lo,

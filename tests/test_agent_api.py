@@ -153,3 +153,54 @@ def test_rollout_forward_and_modes():
     assert torch.allclose(mean.cpu(), ref_mean, atol=1e-4)
     feat = agent.actor.backbone.visual_nn({k: v for k, v in obs.items() if k != "agent"})
     assert torch.allclose(feat.cpu(), f, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_device_replay_ring_matches_a_host_ring():
+    """transitions live in HBM, `sample` draws the reference sampler's indices on the host and
+    gathers on the device straight into the engine's batch buffer (bit-exact data movement)."""
+    from oracle import pointnet_sac_oracle as O
+    from pointcloud_rl_b200.replay import DeviceReplayMemory
+
+    B, N, A, S, cap = 6, 96, 5, 13, 37
+    obs_shape = {"xyz": [3, N], "rgb": [3, N], "seg": [1, N], "agent": S}
+    agent = make_agent("mfrl/drq/maniskill/pn_jitter.py", obs_shape, A, hidden=64, batch_size=B, precision="fp32").to("cuda")
+    ring = DeviceReplayMemory(cap, device="cuda", seed=5)
+    host = None  # numpy mirror with the reference ring's overwrite order (replay_buffer.py:206-231)
+    pos = count = 0
+    for chunk, n in enumerate((20, 1, 25, 9)):  # 55 transitions through a 37-slot ring: wraps once
+        batch = O.synthetic_batch(seed=10 + chunk, B=n, N=N, A=A, n_seg=1, n_pos=0, state_dim=S)
+        flat = {f"{w}/{k}": np.asarray(v) for w in ("obs", "next_obs") for k, v in batch[w].items()}
+        flat.update({k: np.asarray(batch[k]) for k in ("actions", "rewards", "dones")})
+        if host is None:
+            host = {k: np.zeros((cap,) + v.shape[1:], v.dtype) for k, v in flat.items()}
+        if n == 1:
+            ring.push({k: ({kk: vv[0] for kk, vv in v.items()} if isinstance(v, dict) else np.asarray(v)[0]) for k, v in batch.items()})
+        else:
+            ring.push_batch(batch)
+        for i in range(n):
+            for k, v in flat.items():
+                host[k][pos] = v[i]
+            pos, count = (pos + 1) % cap, count + 1
+    assert len(ring) == cap and ring.position == pos
+    twin = np.random.RandomState(5)
+    got = ring.sample(B)
+    idx = twin.randint(0, cap, size=B)
+    assert np.array_equal(got.index, idx)
+    back = got.to_host()
+    for k, v in host.items():
+        node = back
+        for part in k.split("/"):
+            node = node[part]
+        assert np.array_equal(node.astype(v.dtype).reshape(v[idx].shape), v[idx]), k
+    # through the public call: the engine's batch buffer holds exactly the sampled transitions
+    out = agent.update_parameters(ring, 2)
+    assert all(np.isfinite(v) for v in out.values())
+    idx = twin.randint(0, cap, size=B)
+    eng = agent.engine
+    assert np.array_equal(eng.raw["obs"]["xyz"].cpu().numpy(), host["obs/xyz"][idx])
+    assert np.array_equal(eng.raw["next_obs"]["rgb"].cpu().numpy(), host["next_obs/rgb"][idx])
+    assert np.array_equal(eng.raw["obs"]["seg"].cpu().numpy().astype(bool), host["obs/seg"][idx].astype(bool))
+    assert np.array_equal(eng.raw["obs"]["state"].cpu().numpy(), host["obs/agent"][idx])
+    assert np.array_equal(eng.raw["actions"].cpu().numpy(), host["actions"][idx])
+    assert np.array_equal(eng.raw["rewards"].cpu().numpy(), host["rewards"][idx].reshape(-1))
