@@ -257,7 +257,12 @@ class UpdateEngine:
         self.w = w
         self._graphs = {}
         self.graph_calls = {}
-        self._side = [torch.cuda.Stream(device=dev) for _ in range(9)] if dev.type == "cuda" else []
+        # side streams 0-2 carry branches of the critical chain (target branch, second Q head): high priority, like the
+        # capture stream; 3-8 carry the weight-gradient GEMMs that only feed the optimizer: default (low) priority, so
+        # the block scheduler hands free SMs to the dX chain first
+        self._side = ([torch.cuda.Stream(device=dev, priority=-1 if i < 3 else 0) for i in range(9)]
+                      if dev.type == "cuda" else [])
+        self._capture_stream = torch.cuda.Stream(device=dev, priority=-1) if dev.type == "cuda" else None
         self._landing = None
 
     # ------------------------------------------------------------------ parameters
@@ -378,20 +383,23 @@ class UpdateEngine:
         self.L.linear_fwd(h1, h1n, p[f"{net}.w1"], p[f"{net}.b1"], h2, h2n, M, h1n, h2n, 1, self.tf32, st)
         self.L.linear_fwd(h2, h2n, p[f"{net}.w2"], p[f"{net}.b2"], out, ldo, M, h2n, nout, 0, self.tf32, st)
 
-    def _mlp_bwd(self, net, x, K, M, dout, lddo, nout, keep, dx, want_w, st, scratch="a", wstream=None):
+    def _mlp_bwd(self, net, x, K, M, dout, lddo, nout, keep, dx, want_w, st, scratch="a", wstream=None, defer=False):
         """Backward of one 3-layer head.  The data-gradient chain (dX of layer 3 -> 2 -> 1) is the critical path; the
-        weight/bias gradients only feed the optimizer, so with `wstream` (a side-stream index) they are enqueued on
-        forked streams (`wstream`: three side-stream indices), each behind the dY it needs, and joined at the end."""
+        weight/bias gradients only feed the optimizer, so with `wstream` (three side-stream indices) they run on forked
+        streams.  defer=False: each is forked as soon as its dY exists and all are joined before returning.
+        defer=True: they are enqueued after the whole dX chain (they no longer take SMs away from it) and the side
+        streams are returned; the caller joins them (`_join`) before the optimizer step."""
         p, g, (h1n, h2n) = self.p, self.g, self.spec.hidden
         h1, h2 = self.w[f"h1_{keep}"], self.w[f"h2_{keep}"]
         w = {"dh1": self.w[f"dh1_{scratch}"], "dh2": self.w[f"dh2_{scratch}"]}
         L = self.L
         sides = [self._side[i] for i in wstream] if (want_w and wstream is not None) else None
         main = torch.cuda.current_stream()
+        pending = []
 
         def wgrad(xin, ldx, name, dy, lddy, Kin, Nout_):
-            """dW/db of one layer (dy is complete on the main stream when this is called); every layer has its own
-            side stream, so the three weight-gradient GEMMs of a head also overlap each other."""
+            """dW/db of one layer (dy is complete on the main stream when this runs); every layer has its own side
+            stream, so the three weight-gradient GEMMs of a head also overlap each other."""
             if not want_w:
                 return
             side = sides[name] if sides is not None else None
@@ -404,20 +412,32 @@ class UpdateEngine:
                 L.linear_bwd(xin, ldx, p[f"{net}.w{name}"], dy, lddy, g[f"{net}.w{name}"], g[f"{net}.b{name}"], None, 0,
                              None, 0, M, Kin, Nout_, self.tf32, stream_ptr())
 
+        def maybe(*a):
+            if defer and sides is not None:
+                pending.append(a)
+            else:
+                wgrad(*a)
+
         # each layer's dX GEMM applies the previous ReLU's backward in its epilogue (mask = saved post-activation)
-        wgrad(h2, h2n, 2, dout, lddo, h2n, nout)
+        maybe(h2, h2n, 2, dout, lddo, h2n, nout)
         L.linear_bwd(h2, h2n, p[f"{net}.w2"], dout, lddo, None, None, w["dh2"], h2n, h2, h2n, M, h2n, nout, self.tf32,
                      stream_ptr())
-        wgrad(h1, h1n, 1, w["dh2"], h2n, h1n, h2n)
+        maybe(h1, h1n, 1, w["dh2"], h2n, h1n, h2n)
         L.linear_bwd(h1, h1n, p[f"{net}.w1"], w["dh2"], h2n, None, None, w["dh1"], h1n, h1, h1n, M, h1n, h2n, self.tf32,
                      stream_ptr())
-        wgrad(x, x.stride(0), 0, w["dh1"], h1n, K, h1n)
+        maybe(x, x.stride(0), 0, w["dh1"], h1n, K, h1n)
         if dx is not None:
             L.linear_bwd(x, x.stride(0), p[f"{net}.w0"], w["dh1"], h1n, None, None, dx, dx.stride(0), None, 0, M, K, h1n,
                          self.tf32, stream_ptr())
-        if sides is not None:
-            for side in sides:
-                main.wait_stream(side)
+        for a in pending:
+            wgrad(*a)
+        if sides is None:
+            return []
+        if defer:
+            return sides
+        for side in sides:
+            main.wait_stream(side)
+        return []
 
     def _adam(self, group, idx, lr, betas, gradsq_slot, polyak, st):
         lo, hi = self.layout.group_range[group]
@@ -507,10 +527,15 @@ class UpdateEngine:
         L.critic_loss(w["q_obs"], w["y"], R, w["dq"], self.scalars, ST())
 
         # ---- critic backward: the two heads in parallel, their feature gradients add (sac.py:141-142)
+        # single GPU: the heads' weight gradients are deferred behind the dX chains and joined before Adam; with a
+        # gradient all-reduce they are joined here, so the reduction of the Q heads can overlap the PointNet backward
+        defer = self.allreduce is None
         s_q = self._fork(2)
         with torch.cuda.stream(s_q):
-            self._mlp_bwd("q1", cat, ld_cat, R, w["dq"][:, 1:], 2, 1, "q1", w["dx1"], True, ST(), "b", wstream=(3, 4, 5))
-        self._mlp_bwd("q0", cat, ld_cat, R, w["dq"], 2, 1, "q0", w["dx0"], True, ST(), "a", wstream=(6, 7, 8))
+            wg1 = self._mlp_bwd("q1", cat, ld_cat, R, w["dq"][:, 1:], 2, 1, "q1", w["dx1"], True, ST(), "b",
+                                wstream=(3, 4, 5), defer=defer)
+        wg0 = self._mlp_bwd("q0", cat, ld_cat, R, w["dq"], 2, 1, "q0", w["dx0"], True, ST(), "a", wstream=(6, 7, 8),
+                            defer=defer)
         self._join(s_q)
         q_pending = None
         if self.allreduce is not None:
@@ -532,6 +557,7 @@ class UpdateEngine:
         if self.allreduce is not None:
             self.allreduce(self.grads[c_lo:c_lo + self.layout.q_range[0]])  # PointNet gradients (0.3 MB)
             q_pending.wait()
+        self._join(*wg0, *wg1)
         self._adam("critic", 0, hp.lr, hp.betas, 4, do_target, ST())  # + Polyak fused (sac.py:207-208)
 
         # ---- actor + alpha step: sac.py:161-205 / drq.py:114-155
@@ -601,7 +627,7 @@ class UpdateEngine:
                 dst.copy_(src)
             g = torch.cuda.CUDAGraph()
             n0 = self.L.launches
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=self._capture_stream):
                 self.update(updates)
             self.graph_calls[key] = self.L.launches - n0  # C-ABI calls (>= 1 kernel each) replayed per launch
             # capture does not execute: state is untouched
