@@ -527,9 +527,10 @@ class UpdateEngine:
         L.critic_loss(w["q_obs"], w["y"], R, w["dq"], self.scalars, ST())
 
         # ---- critic backward: the two heads in parallel, their feature gradients add (sac.py:141-142)
-        # single GPU: the heads' weight gradients are deferred behind the dX chains and joined before Adam; with a
-        # gradient all-reduce they are joined here, so the reduction of the Q heads can overlap the PointNet backward
-        defer = self.allreduce is None
+        # the heads' weight gradients are deferred behind the dX chains (they would take SMs away from them) and joined
+        # before Adam -- or, with a gradient all-reduce, before the Q heads' reduction, which is issued from a side
+        # stream so that neither the weight gradients nor NCCL hold up the PointNet backward on the compute stream
+        defer = True
         s_q = self._fork(2)
         with torch.cuda.stream(s_q):
             wg1 = self._mlp_bwd("q1", cat, ld_cat, R, w["dq"][:, 1:], 2, 1, "q1", w["dx1"], True, ST(), "b",
@@ -539,10 +540,15 @@ class UpdateEngine:
         self._join(s_q)
         q_pending = None
         if self.allreduce is not None:
-            # the two Q heads' gradients (97 % of the critic bytes) are final here: reduce them on NCCL's stream
-            # while the PointNet head + sparse backward still run on the compute stream
+            # the two Q heads' gradients (97 % of the critic bytes) are final once their weight-gradient streams are:
+            # reduce them on NCCL's stream while the PointNet head + sparse backward still run on the compute stream
             q_lo, q_hi = self.layout.q_range
-            q_pending = self.allreduce(self.grads[c_lo + q_lo:c_lo + q_hi], async_op=True)
+            s_r = self._side[1]  # idle since the target branch joined
+            for s_w in (*wg0, *wg1):
+                s_r.wait_stream(s_w)
+            with torch.cuda.stream(s_r):
+                q_pending = self.allreduce(self.grads[c_lo + q_lo:c_lo + q_hi], async_op=True)
+            wg0, wg1 = [s_r], []
         L.add_cols(w["dx0"], ld_cat, w["dx1"], ld_cat, w["dz"], D, R, D, ST())  # both heads' d/dfeature add up
         L.layernorm_bwd(w["dz"], D, w["xhat_obs"], w["rstd_obs"], p["pn.gf"], self.g["pn.gf"], self.g["pn.bef"],
                         w["dz"], R, D, ST())
