@@ -486,14 +486,19 @@ class UpdateEngine:
         ld_cat = D + S + A
         target_entropy = float(hp.target_entropy) if hp.target_entropy is not None else -float(A)
 
-        self._pack_weights(ST())
-        if self.actor_w0p is not None:  # refreshed every update: the parameters may have been written from outside
-            L.copy_cols(p["actor.w0"], D + S, 1, 1, self.actor_w0p, self.actor_w0p.shape[1], 0, sp.hidden[0], D + S, ST())
+        # weight packing only feeds the encodes: it runs beside the two staging kernels
+        s_p = self._fork(3)
+        with torch.cuda.stream(s_p):
+            self._pack_weights(ST())
+            if self.actor_w0p is not None:  # refreshed every update: the parameters may have been written from outside
+                L.copy_cols(p["actor.w0"], D + S, 1, 1, self.actor_w0p, self.actor_w0p.shape[1], 0, sp.hidden[0], D + S,
+                            ST())
 
         # ---- branch T (side stream 0): TD target, no grad -- sac.py:108-134 / drq.py:71-87
         s_t = self._fork(0)
         with torch.cuda.stream(s_t):
             self._stage("next_obs", "next", k, aug, noise.get(f"{nkey}_next") if nkey else None, 1, ST())
+            s_t.wait_stream(s_p)
             self._encode("next", R, False, ST())
             cat = w["cat_next"]
             if S:
@@ -512,6 +517,7 @@ class UpdateEngine:
 
         # ---- critic forward on the main stream: sac.py:136 / drq.py:89
         self._stage("obs", "obs", k, aug, noise.get(f"{nkey}_obs") if nkey else None, 0, ST())
+        self._join(s_p)
         self._encode("obs", R, True, ST())
         cat = w["cat_obs"]
         if S:
