@@ -183,7 +183,7 @@ def reference_arm(args, w, rank):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    B_s = max(8, w["B"] // 16)
+    B_s = max(8, w["B"] // 4)  # same slice as the native arm's cpu_baseline
     t = run_cpu_update(w, B_s, args.steps, max(1, min(args.warmup, 2)), cores)
     t_full = t * (w["B"] / B_s)  # a full-batch step costs B/B_s sampled steps (per-sample work dominates)
     pts = encoded_points_per_update(w)
