@@ -284,6 +284,14 @@ def test_pointnet_fwd_bf16_tcgen05(L, name):
     pooled2 = torch.empty_like(pooled)
     L.pointnet_fwd_bf16(xh, R, N, NP, wpack, c1, c2, c3, 1e-6, keys, pooled2, None, sp())
     assert torch.equal(pooled, pooled2)
+    # strided source (DrQ's actor step encodes every num_aug-th staged cloud in place): same bits as clouds 0, 2, ...
+    if R >= 3:
+        Rs = (R + 1) // 2
+        pooled3 = torch.empty(Rs, c3, device="cuda")
+        argmax3 = torch.empty(Rs, c3, dtype=torch.int32, device="cuda")
+        L.pointnet_fwd_bf16_strided(xh, Rs, 2, N, NP, wpack, c1, c2, c3, 1e-6, keys, pooled3, argmax3, sp())
+        assert torch.equal(pooled3, pooled[0::2]) and torch.equal(argmax3, argmax[0::2])
+    assert int(keys.abs().max()) == 0  # the scratch is left zeroed for the next call
 
 
 @pytest.mark.parametrize("tf32", [0, 1])
