@@ -19,6 +19,7 @@
 // band of the tile over all S peers through distributed shared memory and applies the epilogue.  No atomics, no
 // global workspace, fixed summation order.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_gemm.cuh"
@@ -275,6 +276,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int z, i0, j0, kb0, nkb;
       if (!tile_coords(t, z, i0, j0, kb0, nkb)) continue;
       const uint32_t buf = n & 1;
+      // ReLU-backward mask of this tile as bits, fetched BEFORE waiting for the accumulator: the loads do not depend on
+      // the MMAs, and issued inside the store loop they are eight dependent HBM round trips per tile (+35 us on the
+      // 100 k-row dgrad GEMMs).  Bit (k*4+e) of mb[c/32][half]: mask > 0 at row k*8 + lane/4, column
+      // c + half*16 + (lane%4)*4 + e -- the post-transpose ownership used below.  Loads are unconditional (clamped
+      // addresses) so that all eight of a chunk are in flight together.
+      uint32_t mb00 = 0, mb01 = 0, mb10 = 0, mb11 = 0, mb20 = 0, mb21 = 0, mb30 = 0, mb31 = 0;
+      const bool mask_fast = S == 1 && P.mask && P.bn <= 128 && (P.ldmask & 3) == 0 && (P.N & 3) == 0 && P.N >= 4 &&
+                             (reinterpret_cast<uintptr_t>(P.mask) & 15) == 0 && (j0 & 3) == 0;
+      if (mask_fast) {
+        const int rr_ = lane >> 2, rs_ = lane & 3;
+        auto fetch = [&](int cc, uint32_t& b0, uint32_t& b1) {
+          if (cc * 32 >= P.bn) return;
+          float4 m[2][4];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int col = min(j0 + cc * 32 + half * 16 + rs_ * 4, P.N - 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int grow = min(i0 + q * 32 + k * 8 + rr_, P.M - 1);
+              m[half][k] = __ldg(reinterpret_cast<const float4*>(P.mask + (int64_t)grow * P.ldmask + col));
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            b0 |= ((m[0][k].x > 0.f ? 1u : 0u) | (m[0][k].y > 0.f ? 2u : 0u) | (m[0][k].z > 0.f ? 4u : 0u) | (m[0][k].w > 0.f ? 8u : 0u)) << (4 * k);
+            b1 |= ((m[1][k].x > 0.f ? 1u : 0u) | (m[1][k].y > 0.f ? 2u : 0u) | (m[1][k].z > 0.f ? 4u : 0u) | (m[1][k].w > 0.f ? 8u : 0u)) << (4 * k);
+          }
+        };
+        fetch(0, mb00, mb01);
+        fetch(1, mb10, mb11);
+        fetch(2, mb20, mb21);
+        fetch(3, mb30, mb31);
+      }
       mbar_wait(ACC_FULL(buf), (n >> 1) & 1);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)P.bn;
@@ -329,7 +363,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             float* crow = P.C + (int64_t)grow * P.ldc + col;
             const bool full = col + 4 <= P.N;
             float mk[4] = {1.f, 1.f, 1.f, 1.f};
-            if (P.mask) {
+            if (mask_fast) {
+              const int cc = c >> 5;
+              const uint32_t word = half == 0 ? (cc == 0 ? mb00 : cc == 1 ? mb10 : cc == 2 ? mb20 : mb30)
+                                              : (cc == 0 ? mb01 : cc == 1 ? mb11 : cc == 2 ? mb21 : mb31);
+              const uint32_t b4 = word >> (4 * k);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) mk[e] = (b4 >> e) & 1u ? 1.f : 0.f;
+            } else if (P.mask) {
               const float* mrow = P.mask + (int64_t)grow * P.ldmask + col;
               if (full && (reinterpret_cast<uintptr_t>(mrow) & 15) == 0) {
                 const float4 m4 = __ldg(reinterpret_cast<const float4*>(mrow));
@@ -564,7 +605,9 @@ int launch_tc_gemm(const TcGemmArgs& g, cudaStream_t st) {
   if (kb_max < 1) return PCRL_OK;
   // ring depth: enough to cover the K loop of a tile (plus prefetch into the next tile), capped by smem; short-K
   // tall-skinny problems keep the ring small so two CTAs fit on an SM
-  const int64_t budget = (n_tiles >= 2 * sms && kb_max <= 8) ? 100 * 1024 : 200 * 1024;
+  static const char* env_b = getenv("PCRL_GEMM_BUDGET_KB");  // experiment knob
+  int64_t budget = (n_tiles >= 2 * sms && kb_max <= 8) ? 100 * 1024 : 200 * 1024;
+  if (env_b) budget = atoi(env_b) * 1024;
   P.stages = (int)std::min<int64_t>(std::min<int64_t>(8, std::max<int64_t>(3, 2 * kb_max)), std::max<int64_t>(2, budget / stage_bytes));
   const size_t smem = (size_t)P.stages * stage_bytes + 8 * (2 * P.stages + 5) + 32 + 8192 + 1024;
   const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / smem));
