@@ -19,7 +19,6 @@
 // band of the tile over all S peers through distributed shared memory and applies the epilogue.  No atomics, no
 // global workspace, fixed summation order.
 #include <cuda.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_gemm.cuh"
@@ -605,9 +604,7 @@ int launch_tc_gemm(const TcGemmArgs& g, cudaStream_t st) {
   if (kb_max < 1) return PCRL_OK;
   // ring depth: enough to cover the K loop of a tile (plus prefetch into the next tile), capped by smem; short-K
   // tall-skinny problems keep the ring small so two CTAs fit on an SM
-  static const char* env_b = getenv("PCRL_GEMM_BUDGET_KB");  // experiment knob
-  int64_t budget = (n_tiles >= 2 * sms && kb_max <= 8) ? 100 * 1024 : 200 * 1024;
-  if (env_b) budget = atoi(env_b) * 1024;
+  const int64_t budget = (n_tiles >= 2 * sms && kb_max <= 8) ? 100 * 1024 : 200 * 1024;
   P.stages = (int)std::min<int64_t>(std::min<int64_t>(8, std::max<int64_t>(3, 2 * kb_max)), std::max<int64_t>(2, budget / stage_bytes));
   const size_t smem = (size_t)P.stages * stage_bytes + 8 * (2 * P.stages + 5) + 32 + 8192 + 1024;
   const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / smem));
