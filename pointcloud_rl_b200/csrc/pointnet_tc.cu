@@ -163,17 +163,40 @@ __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
   return d;
 }
 
-// sum and sum of squares of one 32-column chunk, 4 independent dependency chains
+// Packed fp32 pairs (sm_100 FFMA2, `fma.rn.f32x2`): same FMA-pipe throughput as two scalar FFMAs but ONE issue slot, and
+// issue slots -- not the FMA pipe -- are what the epilogues run out of.
+__device__ __forceinline__ uint64_t pk2(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pk2f(float lo, float hi) { return pk2(__float_as_uint(lo), __float_as_uint(hi)); }
+__device__ __forceinline__ void unpk2(uint64_t p, uint32_t& lo, uint32_t& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(p));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+// sum and sum of squares of one 32-column chunk, 4 independent dependency chains (two packed pairs each)
 __device__ __forceinline__ void stats32(const uint32_t (&v)[32], float (&s)[4], float (&q)[4]) {
+  const uint64_t one2 = pk2f(1.f, 1.f);
+  uint64_t s01 = pk2f(s[0], s[1]), s23 = pk2f(s[2], s[3]), q01 = pk2f(q[0], q[1]), q23 = pk2f(q[2], q[3]);
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float y = __uint_as_float(v[j + e]);
-      s[e] += y;
-      q[e] = fmaf(y, y, q[e]);
-    }
+    const uint64_t y01 = pk2(v[j], v[j + 1]), y23 = pk2(v[j + 2], v[j + 3]);
+    s01 = fma2(y01, one2, s01);
+    s23 = fma2(y23, one2, s23);
+    q01 = fma2(y01, y01, q01);
+    q23 = fma2(y23, y23, q23);
   }
+  uint32_t a, b;
+  unpk2(s01, a, b); s[0] = __uint_as_float(a); s[1] = __uint_as_float(b);
+  unpk2(s23, a, b); s[2] = __uint_as_float(a); s[3] = __uint_as_float(b);
+  unpk2(q01, a, b); q[0] = __uint_as_float(a); q[1] = __uint_as_float(b);
+  unpk2(q23, a, b); q[2] = __uint_as_float(a); q[3] = __uint_as_float(b);
 }
 
 // Dump-mode store of one 32x32 fp32 chunk.  After tcgen05.ld every thread holds 32 consecutive floats of ITS row, so a
@@ -498,17 +521,18 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
         if (d_x1 && h == 0) dump.rstd1[tile * 128 + row] = rstd;
         for (int ch = col0; ch < col0 + (c2 >> 1); ch += 32) {
           tmem_ld32(tlane + ch, v);
+          {
+            const uint64_t r2 = pk2f(rstd, rstd), n2 = pk2f(nmr, nmr);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), rstd, nmr));  // xhat
+            for (int j = 0; j < 32; j += 2) unpk2(fma2(pk2(v[j], v[j + 1]), r2, n2), v[j], v[j + 1]);  // xhat
+          }
           if (d_x1) dump_chunk32(dscr, d_x1 + ch, c2, v, lane);
 #pragma unroll
           for (int j4 = 0; j4 < 32; j4 += 4) {
             const float4 gg = *reinterpret_cast<const float4*>(g1 + ch + j4);
             const float4 bb = *reinterpret_cast<const float4*>(be1 + ch + j4);
-            v[j4] = __float_as_uint(fmaf(__uint_as_float(v[j4]), gg.x, bb.x));
-            v[j4 + 1] = __float_as_uint(fmaf(__uint_as_float(v[j4 + 1]), gg.y, bb.y));
-            v[j4 + 2] = __float_as_uint(fmaf(__uint_as_float(v[j4 + 2]), gg.z, bb.z));
-            v[j4 + 3] = __float_as_uint(fmaf(__uint_as_float(v[j4 + 3]), gg.w, bb.w));
+            unpk2(fma2(pk2(v[j4], v[j4 + 1]), pk2f(gg.x, gg.y), pk2f(bb.x, bb.y)), v[j4], v[j4 + 1]);
+            unpk2(fma2(pk2(v[j4 + 2], v[j4 + 3]), pk2f(gg.z, gg.w), pk2f(bb.z, bb.w)), v[j4 + 2], v[j4 + 3]);
           }
           if (d_h1) {
 #pragma unroll
@@ -674,11 +698,14 @@ pointnet_fwd_tc_kernel(const char* __restrict__ xh, const char* __restrict__ wpa
           const int nb = n_pos - (cbase + ch);
           if (nb >= 32 || nb <= 0) {
             const float add = nb > 0 ? add_pos : add_neg;
+            const uint64_t r2 = pk2f(rstd, rstd), a2 = pk2f(add, add);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              asm("lop3.b32 %0, %1, 0xffffffe0, %2, 0xea;"  // (z & ~31) | tag
-                  : "=r"(v[j])
-                  : "r"(__float_as_uint(fmaf(__uint_as_float(v[j]), rstd, add))), "r"(lane_tag));
+            for (int j = 0; j < 32; j += 2) {
+              uint32_t z0, z1;
+              unpk2(fma2(pk2(v[j], v[j + 1]), r2, a2), z0, z1);
+              asm("lop3.b32 %0, %1, 0xffffffe0, %2, 0xea;" : "=r"(v[j]) : "r"(z0), "r"(lane_tag));  // (z & ~31) | tag
+              asm("lop3.b32 %0, %1, 0xffffffe0, %2, 0xea;" : "=r"(v[j + 1]) : "r"(z1), "r"(lane_tag));
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
