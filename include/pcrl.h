@@ -40,6 +40,9 @@ extern "C" {
                              (pcd_aug.py:192-197, apply_rot_trans :84-123).  Axes: bits 8..10 of aug_kind select the
                              shifted axes (x,y,z), 0 = all three -- dm_control/pn_shift.py uses [0.04, 0, 0.04] */
 #define PCRL_AUG_SHIFT_AXES(mask) (PCRL_AUG_SHIFT | ((mask) << 8))
+#define PCRL_AUG_DOWNSAMPLE 4 /* RandomDownSample (pn_dropout.py; pcd_aug.py:240-257): one random subset of the points
+                                 per call, shared by all clouds.  `noise` is REQUIRED: an int32 source map [N] (kept point
+                                 -> itself, dropped point -> a kept one), from pcrl_downsample_map or the caller */
 
 int pcrl_abi_version(void);
 const char* pcrl_last_error(void);
@@ -68,6 +71,12 @@ int pcrl_stage_points(const float* xyz, const void* rgb, int rgb_is_u8, const ui
                       const uint8_t* seg, int n_seg, int B, int N, int repeat, int aug_kind, float aug_lo,
                       float aug_hi, const float* noise, uint64_t seed, const uint64_t* counter_dev,
                       uint32_t stream_id, float* xf, void* xh, int CP, void* stream);
+
+/* RandomDownSample's random subset drawn on the device (Philox keyed by seed, *counter_dev, stream_id): n_drop =
+ * int(N*drop_ratio) if fixed_ratio else uniform in [0, int(N*drop_ratio)), keep the N - n_drop points with the smallest
+ * random keys (pcd_aug.py:244-251, array_ops.py:659-673).  src_map: int32 [N] for pcrl_stage_points.  N <= 4096. */
+int pcrl_downsample_map(int N, float drop_ratio, int fixed_ratio, uint64_t seed, const uint64_t* counter_dev,
+                        uint32_t stream_id, int32_t* src_map, void* stream);
 
 /* Device-resident replay sampling (replaces ReplayMemory.sample's numpy `take` per key + the per-leaf H2D copies,
  * replay_buffer.py:297-322, dict_array.py:308-318): for every leaf l of a transition, dst_l[b] = src_l[idx[b]].

@@ -186,6 +186,12 @@ def aug_shift(xyz, shift):
     return xyz + shift[:, :, None]
 
 
+def aug_downsample(obs, index):
+    """RandomDownSample.process_single, pcd_aug.py:240-257: every point-cloud key keeps the same `index` subset of its
+    points (`DictArray(data).slice(index, -1)`); index [N'] int64 (the argsort-of-rand draw is injected)."""
+    return {k: (v[..., index] if k in ("xyz", "rgb", "seg", "pos_encoding") else v) for k, v in obs.items()}
+
+
 def _apply_aug(obs, hp, noise, which):
     obs = dict(obs)
     kind = hp.get("aug", None)
@@ -195,6 +201,8 @@ def _apply_aug(obs, hp, noise, which):
         obs["xyz"] = aug_rot_z(obs["xyz"], noise[f"angle_{which}"])
     elif kind == "shift":
         obs["xyz"] = aug_shift(obs["xyz"], noise[f"shift_{which}"])
+    elif kind == "downsample":
+        obs = aug_downsample(obs, noise[f"keep_{which}"].long())
     elif kind is not None:
         raise ValueError(kind)
     return obs
@@ -294,7 +302,7 @@ def update(state, batch, updates, hp, noise, capture=None):
 
     batch: dict(obs=dict, next_obs=dict, actions [B,A], rewards [B,1], dones [B,1]) of numpy / torch.
     noise: injected randomness -- jitter_obs / jitter_next [B*num_aug,3,N] (or angle_obs / angle_next
-           [B*num_aug,1], or shift_obs / shift_next [B*num_aug,3]), eps_next [B*num_aug,A], eps_pi [B,A].
+           [B*num_aug,1], or shift_obs / shift_next [B*num_aug,3], or keep_obs / keep_next [N'] kept point indices), eps_next [B*num_aug,A], eps_pi [B,A].
     Mutates `state` in place, returns the reference's scalar dict.  `capture` (a dict) receives
     intermediates for the parity tests.
     """

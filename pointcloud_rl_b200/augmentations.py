@@ -110,6 +110,43 @@ class GlobalRotScaleTrans(BaseAugmentation):
         return f"GlobalRotScaleTrans(translation={self.shift}, axes={self.axes:03b})"
 
 
+@AUGMENTATIONS.register_module()
+class RandomDownSample(BaseAugmentation):
+    """One random subset of the points per call, shared by all clouds and applied to every point-cloud key
+    (pcd_aug.py:228-268; `pn_dropout.py`: drop_ratio=0.3, fixed_ratio=False).  The update path keeps the staged shape:
+    dropped points are replaced by a kept one, which leaves the max-pooled features unchanged."""
+
+    kind = "downsample"
+
+    def __init__(self, main_key="inputs/xyz", req_keys=None, max_num_points=None, drop_ratio=None, fixed_ratio=True):
+        super().__init__(main_key, req_keys)
+        if max_num_points is not None or drop_ratio is None:
+            raise NotImplementedError("RandomDownSample: only the drop_ratio form (pn_dropout.py) is supported")
+        if not 0.0 <= float(drop_ratio) < 1.0:
+            raise ValueError("drop_ratio must be in [0, 1)")
+        self.drop_ratio, self.fixed_ratio = float(drop_ratio), bool(fixed_ratio)
+
+    def params(self):
+        return self.kind, self.drop_ratio, float(self.fixed_ratio)
+
+    def __call__(self, data):
+        data = dict(data)
+        index = None
+        for key in self.req_keys:
+            if key in data:
+                x = data[key]
+                if index is None:
+                    N = x.shape[-1]
+                    hi = int(N * self.drop_ratio)
+                    n_drop = hi if self.fixed_ratio else (int(torch.randint(hi, (1,)).item()) if hi > 0 else 0)
+                    index = torch.rand(N, device=x.device).argsort()[: N - n_drop]
+                data[key] = x[..., index]
+        return data
+
+    def __repr__(self):
+        return f"RandomDownSample(drop_ratio={self.drop_ratio}, fixed_ratio={self.fixed_ratio})"
+
+
 class DataAugmentations:
     def __init__(self, transforms):
         self.transforms = [build_from_cfg(t, AUGMENTATIONS) if isinstance(t, dict) else t for t in transforms]

@@ -87,3 +87,7 @@ ROT_Z = dict(type="GlobalRotScaleTrans", main_key="xyz", req_keys=["xyz"], rot_r
 def shift(translation_range):
     return dict(type="GlobalRotScaleTrans", main_key="xyz", req_keys=["xyz"], rot_range=None, scale_ratio_range=None,
                 translation_range=list(translation_range), shift_height=True)
+
+
+def dropout(req_keys):
+    return dict(type="RandomDownSample", main_key="xyz", req_keys=list(req_keys), drop_ratio=0.3, fixed_ratio=False)

@@ -26,7 +26,10 @@ __global__ void __launch_bounds__(256) stage_points_kernel(
   const int b = (int)(t / NP), n_out = (int)(t % NP);
   // padding rows (n_out >= N) replicate the cloud's point 0, augmentation draw included: a duplicate can only
   // tie with the real point and the smallest-index rule of the max-pool then drops it (no masking downstream)
-  const int n = n_out < N ? n_out : 0;
+  int n = n_out < N ? n_out : 0;
+  // RandomDownSample: dropped points are replaced by a kept one (noise = int32 source map [N]); a duplicate can only tie
+  // with its original in the max-pool, so the pooled features equal those of the sliced cloud
+  if (aug_kind == PCRL_AUG_DOWNSAMPLE) n = reinterpret_cast<const int32_t*>(noise)[n];
   const int C = 3 + (rgb ? 3 : 0) + n_pos + n_seg;
   const uint64_t cnt = counter_dev ? *counter_dev : 0ull;
 
@@ -152,6 +155,39 @@ __global__ void __launch_bounds__(256) stage_points_kernel(
   }
 }
 
+// RandomDownSample's draw on the device (pcd_aug.py:240-257; array_ops.py:659-673): one random subset of the points,
+// shared by every cloud of the call.  n_drop = int(N*ratio) (fixed_ratio) or uniform in [0, int(N*ratio)); the kept
+// points are the N - n_drop smallest of N random keys (the reference argsorts torch.rand).  Output: src[i] = i for a
+// kept point, else the kept point of rank 0.  One block; N <= 4096 (keys in shared memory, O(N^2) ranking).
+__global__ void __launch_bounds__(1024) downsample_map_kernel(int N, float ratio, int fixed_ratio, uint64_t seed,
+                                                              const uint64_t* __restrict__ counter_dev, uint32_t stream_id,
+                                                              int32_t* __restrict__ src) {
+  __shared__ uint32_t key[4096];
+  __shared__ int first;
+  const uint64_t cnt = counter_dev ? *counter_dev : 0ull;
+  const uint2 k2 = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
+    key[i] = philox4x32_10(make_uint4((uint32_t)i, 0xFFFFFFFDu, (uint32_t)cnt, (uint32_t)(cnt >> 32) ^ (stream_id << 24)), k2).x;
+  const int hi = (int)((float)N * ratio);
+  int n_drop = hi;
+  if (!fixed_ratio) {
+    const uint32_t r = philox4x32_10(make_uint4(0xFFFFFFFFu, 0xFFFFFFFDu, (uint32_t)cnt, (uint32_t)(cnt >> 32) ^ (stream_id << 24)), k2).y;
+    n_drop = hi > 0 ? (int)(((uint64_t)r * (uint64_t)hi) >> 32) : 0;
+  }
+  const int n_keep = max(N - n_drop, 1);
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const uint32_t ki = key[i];
+    int rank = 0;
+    for (int j = 0; j < N; ++j) rank += (key[j] < ki) || (key[j] == ki && j < i);
+    if (rank == 0) first = i;
+    src[i] = rank < n_keep ? i : -1;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
+    if (src[i] < 0) src[i] = first;
+}
+
 // Replay sampling on the device: dst_leaf[b] = src_leaf[idx[b]] for every leaf of a transition, one launch.
 // blockIdx.y = leaf, blockIdx.x = sampled row; rows are copied as 16-byte vectors when both sides allow it.
 __global__ void __launch_bounds__(256) gather_transitions_kernel(const unsigned long long* __restrict__ src_ptrs,
@@ -178,6 +214,18 @@ __global__ void __launch_bounds__(256) gather_transitions_kernel(const unsigned 
 
 using namespace pcrl;
 
+extern "C" int pcrl_downsample_map(int N, float drop_ratio, int fixed_ratio, uint64_t seed, const uint64_t* counter_dev,
+                                   uint32_t stream_id, int32_t* src_map, void* stream) {
+  PCRL_CHECK_ARG(src_map && N >= 1 && drop_ratio >= 0.f && drop_ratio < 1.f);
+  if (N > 4096) {
+    set_error("pcrl_downsample_map: N = %d > 4096 points is not supported by the device-side draw", N);
+    return PCRL_EUNSUPPORTED;
+  }
+  downsample_map_kernel<<<1, 1024, 0, as_stream(stream)>>>(N, drop_ratio, fixed_ratio, seed, counter_dev, stream_id, src_map);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
+
 extern "C" int pcrl_gather_transitions(const uint64_t* src_ptrs, const uint64_t* dst_ptrs, const int64_t* row_bytes,
                                        int n_leaves, const int64_t* idx, int B, void* stream) {
   PCRL_CHECK_ARG(src_ptrs && dst_ptrs && row_bytes && idx && n_leaves >= 1 && B >= 0);
@@ -199,7 +247,8 @@ extern "C" int pcrl_stage_points(const float* xyz, const void* rgb, int rgb_is_u
   aug_kind &= 0xff;
   if (axis_mask == 0) axis_mask = 7;
   PCRL_CHECK_ARG(aug_kind == PCRL_AUG_NONE || aug_kind == PCRL_AUG_JITTER || aug_kind == PCRL_AUG_ROTZ ||
-                 aug_kind == PCRL_AUG_SHIFT);
+                 aug_kind == PCRL_AUG_SHIFT || aug_kind == PCRL_AUG_DOWNSAMPLE);
+  PCRL_CHECK_ARG(aug_kind != PCRL_AUG_DOWNSAMPLE || noise != nullptr);
   const int C = 3 + (rgb ? 3 : 0) + (pos ? n_pos : 0) + (seg ? n_seg : 0);
   PCRL_CHECK_ARG((CP == 8 || CP == 16) && C <= CP);
   PCRL_CHECK_ARG(!xh || C + 4 <= 16);

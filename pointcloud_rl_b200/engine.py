@@ -22,7 +22,7 @@ S_NAMES = [
     "entropy", "actor_grad_sq", "alpha", "alpha_grad",
 ]
 NUM_SCALARS = 16
-AUG_KINDS = {None: 0, "none": 0, "jitter": 1, "rot": 2, "shift": 3}
+AUG_KINDS = {None: 0, "none": 0, "jitter": 1, "rot": 2, "shift": 3, "downsample": 4}
 MLP_KEYS = ["w0", "b0", "w1", "b1", "w2", "b2"]
 PN_KEYS = ["pn.w0", "pn.b0", "pn.w1", "pn.g1", "pn.be1", "pn.w2", "pn.g2", "pn.be2", "pn.wf", "pn.bf", "pn.gf", "pn.bef"]
 
@@ -216,6 +216,9 @@ class UpdateEngine:
 
         w = {}
         bf16 = self.precision == "bf16"
+        if self.hp.algo == "drq" and self.hp.aug == "downsample":
+            w["ds_map_next"] = torch.zeros(N, dtype=torch.int32, device=dev)
+            w["ds_map_obs"] = torch.zeros(N, dtype=torch.int32, device=dev)
         for name, rows in (("next", R), ("obs", R), ("pi", B)):
             if not bf16 or name == "obs":  # tensor-core path: only the critic's backward reads the fp32 staging
                 w[f"xf_{name}"] = torch.zeros(rows, NP, CP, **f32)
@@ -478,9 +481,24 @@ class UpdateEngine:
         c1, c2, c3 = sp.widths
         noise = noise or {}
         aug = AUG_KINDS[hp.aug] if hp.algo == "drq" else 0
-        nkey = {1: "jitter", 2: "angle", 3: "shift"}.get(aug)
+        nkey = {1: "jitter", 2: "angle", 3: "shift", 4: "keep"}.get(aug)
         if aug == 3:
             aug |= (int(hp.aug_axes) & 7) << 8
+        if aug == 4:
+            # RandomDownSample: the stage kernel takes a source map [N].  Parity mode: built from the injected kept
+            # indices; otherwise drawn on the device (aug_lo = drop_ratio, aug_hi = fixed_ratio)
+            maps = {}
+            for which, sid in (("next", 1), ("obs", 0)):
+                m = w[f"ds_map_{which}"]
+                keep = noise.get(f"keep_{which}")
+                if keep is not None:
+                    keep = keep.to(device=m.device, dtype=torch.int64)
+                    m.fill_(int(keep[0]))
+                    m[keep] = keep.to(torch.int32)
+                else:
+                    L.downsample_map(sp.n_points, float(hp.aug_lo), int(hp.aug_hi != 0), self.seed, self.counter, sid, m, ST())
+                maps[f"keep_{which}"] = m
+            noise = dict(noise, **maps)
         do_actor = updates % hp.actor_update_interval == 0
         do_target = updates % hp.target_update_interval == 0
         ld_cat = D + S + A

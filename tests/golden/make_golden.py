@@ -49,6 +49,7 @@ def draw_noise(seed, algo, aug, k, B, N, A, with_actor, rng):
     from torch.distributions.utils import _standard_normal
 
     torch.manual_seed(seed)
+    np.random.seed(seed % (2**32))  # RandomDownSample draws n_drop from numpy's global RNG (pcd_aug.py:245)
     noise = {}
     if algo == "drq":
         for which in ("obs", "next"):
@@ -56,6 +57,9 @@ def draw_noise(seed, algo, aug, k, B, N, A, with_actor, rng):
                 noise[f"jitter_{which}"] = torch.FloatTensor(B * k, 3, N).uniform_(*rng)
             elif aug == "rot":
                 noise[f"angle_{which}"] = torch.zeros([B * k, 1]).uniform_(*rng)
+            elif aug == "downsample":  # pcd_aug.py:244-251 + array_ops.py:659-673; rng = (drop_ratio, fixed_ratio)
+                n_drop = int(N * rng[0]) if rng[1] else np.random.randint(int(N * rng[0]))
+                noise[f"keep_{which}"] = torch.rand(1, N).argsort(1)[0, : N - n_drop].clone()
             elif aug == "shift":  # pcd_aug.py:193, translation_range = [hi, hi, hi]
                 noise[f"shift_{which}"] = (torch.rand([B * k, 3]) - 0.5) * 2 * torch.tensor([rng[1]] * 3, dtype=torch.float)
     noise["eps_next"] = _standard_normal((B * k, A), dtype=torch.float32, device=torch.device("cpu"))
@@ -96,6 +100,7 @@ def gen_update_fixture(ns, name, cfg_path, algo, aug, aug_rng, B, N, A, n_seg, n
         noise = draw_noise(seed, algo, aug, k, B, N, A, with_actor, aug_rng)
         flatten(f"noise{u}/", noise, out)
         torch.manual_seed(seed)
+        np.random.seed(seed % (2**32))
         ret = agent.update_parameters(mem, updates=u)
         for key, val in ret.items():
             out[f"ret{u}/{key}"] = np.float64(val)
@@ -149,6 +154,10 @@ def gen_pointnet_fixture(ns, name, C_extra, B, N, dup, widths=(128, 128, 256), D
 def main():
     ns = load_reference()
     torch.set_num_threads(8)
+    if "--only-downsample" in sys.argv:  # added after the other fixtures were committed; they are not regenerated
+        gen_update_fixture(ns, "drq_downsample_small", "configs/mfrl/drq/maniskill/pn_dropout.py", "drq", "downsample",
+                           (0.3, 0), B=5, N=80, A=4, n_seg=2, n_pos=0, S=9, dup=False)
+        return
     if "--only-shift" in sys.argv:  # added after the other fixtures were committed; they are not regenerated
         gen_update_fixture(ns, "drq_shift_small", "configs/mfrl/drq/maniskill/pn_shift.py", "drq", "shift", (-0.1, 0.1),
                            B=5, N=72, A=4, n_seg=1, n_pos=0, S=9, dup=False)
@@ -164,6 +173,8 @@ def main():
                        B=4, N=80, A=5, n_seg=3, n_pos=0, S=13, dup=False)
     gen_update_fixture(ns, "drq_shift_small", "configs/mfrl/drq/maniskill/pn_shift.py", "drq", "shift", (-0.1, 0.1),
                        B=5, N=72, A=4, n_seg=1, n_pos=0, S=9, dup=False)
+    gen_update_fixture(ns, "drq_downsample_small", "configs/mfrl/drq/maniskill/pn_dropout.py", "drq", "downsample",
+                       (0.3, 0), B=5, N=80, A=4, n_seg=2, n_pos=0, S=9, dup=False)
 
 
 if __name__ == "__main__":

@@ -204,3 +204,21 @@ def test_device_replay_ring_matches_a_host_ring():
     assert np.array_equal(eng.raw["obs"]["state"].cpu().numpy(), host["obs/agent"][idx])
     assert np.array_equal(eng.raw["actions"].cpu().numpy(), host["actions"][idx])
     assert np.array_equal(eng.raw["rewards"].cpu().numpy(), host["rewards"][idx].reshape(-1))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rel", ["mfrl/drq/maniskill/pn_shift.py", "mfrl/drq/maniskill/pn_dropout.py"])
+def test_widened_augmentation_configs_run_through_the_public_call(rel):
+    """pn_shift.py / pn_dropout.py: agent from the config, graph-replayed updates with the
+    device-side (Philox) draws, finite logged scalars with the reference's keys."""
+    from pointcloud_rl_b200.data import FixedBatchMemory
+    from pointcloud_rl_b200.synthetic import synthetic_batch
+
+    B, N, A, S = 4, 200, 5, 13
+    obs_shape = {"xyz": [3, N], "rgb": [3, N], "seg": [1, N], "agent": S}
+    agent = make_agent(rel, obs_shape, A, hidden=64, batch_size=B).to("cuda")
+    mem = FixedBatchMemory(synthetic_batch(0, B, N, A, n_seg=1, state_dim=S))
+    for u in range(1, 5):
+        out = agent.update_parameters(mem, u)
+        assert all(np.isfinite(v) for v in out.values())
+    assert {"drq/critic_loss", "drq/actor_loss", "drq/alpha_loss", "drq/entropy"} <= set(out)

@@ -196,6 +196,45 @@ def _run_pointnet_f32(L, p, obs, want_argmax=True):
     return x, xf, d, pooled, argmax, (R, N, NP, CP, C, c1, c2, c3)
 
 
+def test_downsample_map_and_staging(L):
+    """RandomDownSample on the device: the drawn subset has the reference's size law, dropped points are replaced by a
+    kept one, and staging through the map reproduces exactly those rows."""
+    N, ratio = 200, 0.3
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    maps = []
+    for c in range(6):
+        cnt.fill_(c)
+        m = torch.full((N,), -7, dtype=torch.int32, device="cuda")
+        L.downsample_map(N, ratio, 0, 11, cnt, 0, m, sp())
+        mc = m.cpu().long()
+        kept = (mc == torch.arange(N))
+        assert N - int(N * ratio) < int(kept.sum()) <= N          # n_drop uniform in [0, int(N * ratio))
+        assert bool(kept[mc].all())                                # every dropped point maps to a kept one
+        assert len(torch.unique(mc[~kept])) <= 1                   # ... the same one
+        maps.append(mc)
+    assert len({int(k.eq(torch.arange(N)).sum()) for k in maps}) > 1  # the kept count varies from call to call
+    m2 = torch.empty(N, dtype=torch.int32, device="cuda")
+    L.downsample_map(N, ratio, 0, 11, cnt, 0, m2, sp())
+    assert torch.equal(m2.cpu().long(), maps[-1])                 # deterministic in (seed, counter, stream)
+    L.downsample_map(N, ratio, 1, 11, cnt, 1, m2, sp())
+    assert int((m2.cpu().long() == torch.arange(N)).sum()) == N - int(N * ratio)  # fixed_ratio: exact count
+    # staging through the map
+    rs = np.random.RandomState(4)
+    B = 3
+    obs = O.synthetic_obs(rs, B, N, n_seg=1, n_pos=0)
+    t = {k: torch.from_numpy(v) for k, v in obs.items()}
+    x_full = O.preprocess(t)                                       # [B, C, N]
+    C = x_full.shape[1]
+    xf = torch.zeros(B, 256, 8, device="cuda")
+    L.stage_points(t["xyz"].cuda(), t["rgb"].cuda(), 1, None, 0, t["seg"].to(torch.uint8).cuda(), 1, B, N, 1, 4, ratio, 0.0,
+                   m2, 0, None, 0, xf, None, 8, sp())
+    src = m2.cpu().long()
+    assert torch.equal(xf[:, :N, :C].permute(0, 2, 1).cpu(), x_full[:, :, src])
+    # the max-pool sees exactly the kept points
+    kept_idx = torch.nonzero(src == torch.arange(N)).flatten()
+    assert torch.equal(xf[:, :N, :C].cpu().amax(1), O.preprocess(O.aug_downsample(t, kept_idx)).amax(2))
+
+
 def test_stage_points_philox_shift_axes(L):
     """Device-side draw of the pn_shift translation: one offset per (cloud, augmentation), uniform in [-t, t], only on
     the axes the mask enables (dm_control/pn_shift.py shifts x and z)."""
@@ -401,7 +440,7 @@ def _engine_from_golden(g, precision="fp32"):
     return eng, m
 
 
-@pytest.mark.parametrize("name", ["sac_dmc_small", "drq_jitter_small", "drq_rot_small", "drq_shift_small"])
+@pytest.mark.parametrize("name", ["sac_dmc_small", "drq_jitter_small", "drq_rot_small", "drq_shift_small", "drq_downsample_small"])
 def test_update_matches_reference_fp32(name):
     g = load_golden(name)
     eng, m = _engine_from_golden(g)
