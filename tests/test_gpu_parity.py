@@ -467,7 +467,7 @@ def test_update_matches_reference_fp32(name):
             assert float((delta - delta_ref).abs().max()) <= 2.1e-3 * u, (u, key)
 
 
-@pytest.mark.parametrize("name", ["sac_dmc_small", "drq_jitter_small"])
+@pytest.mark.parametrize("name", ["sac_dmc_small", "drq_jitter_small", "drq_shift_small", "drq_downsample_small"])
 def test_update_bf16_within_tolerance(name):
     """bf16 tensor-core forward inside the full update: logged scalars within 2e-2 of the reference."""
     g = load_golden(name)
