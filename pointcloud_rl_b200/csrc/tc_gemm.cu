@@ -559,7 +559,7 @@ int launch_tc_gemm(const TcGemmArgs& g, cudaStream_t st) {
     const uint32_t stage_b = BM * BK * 4 + bn * BK * 4;
     const int64_t kb_slice = cdiv(kb_total, cluster_k);
     const size_t red_bytes = (size_t)BM * (bn + 4) * 4;
-    int stages = (int)std::min<int64_t>(8, std::max<int64_t>(2, kb_slice));
+    int stages = (int)std::min<int64_t>(3, std::max<int64_t>(2, kb_slice));  // <= ~105 KB: two CTAs per SM, the heads' GEMMs run 2-3 at a time
     while ((size_t)stages * stage_b < red_bytes) ++stages;
     while ((size_t)stages * stage_b + 12288 > 224 * 1024 && stages > 2) --stages;
     if ((size_t)stages * stage_b < red_bytes) {
@@ -604,7 +604,10 @@ int launch_tc_gemm(const TcGemmArgs& g, cudaStream_t st) {
   if (kb_max < 1) return PCRL_OK;
   // ring depth: enough to cover the K loop of a tile (plus prefetch into the next tile), capped by smem; short-K
   // tall-skinny problems keep the ring small so two CTAs fit on an SM
-  const int64_t budget = (n_tiles >= 2 * sms && kb_max <= 8) ? 100 * 1024 : 200 * 1024;
+  // ring budget: short K loops keep the ring small so that two CTAs fit on an SM -- tall-skinny streaming problems get
+  // twice the CTAs per SM, and the small MLP-head GEMMs, which run two or three at a time on forked streams, do not
+  // lock each other out of the SMs
+  const int64_t budget = (kb_max <= 8) ? 100 * 1024 : 200 * 1024;
   P.stages = (int)std::min<int64_t>(std::min<int64_t>(8, std::max<int64_t>(3, 2 * kb_max)), std::max<int64_t>(2, budget / stage_bytes));
   const size_t smem = (size_t)P.stages * stage_bytes + 8 * (2 * P.stages + 5) + 32 + 8192 + 1024;
   const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / smem));
