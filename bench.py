@@ -183,7 +183,11 @@ def reference_arm(args, w, rank):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    B_s = max(8, w["B"] // 4)  # same slice as the native arm's cpu_baseline
+    # bounded sample: a B/4 slice per step (as the native arm's cpu_baseline) unless K steps of it would run for more
+    # than ~2 minutes (≈ 6 ms of host time per sample on this class of box), then a smaller power-of-two slice
+    B_s = max(8, w["B"] // 4)
+    while B_s > 8 and args.steps * 0.006 * B_s > 120.0:
+        B_s //= 2
     t = run_cpu_update(w, B_s, args.steps, max(1, min(args.warmup, 2)), cores)
     t_full = t * (w["B"] / B_s)  # a full-batch step costs B/B_s sampled steps (per-sample work dominates)
     pts = encoded_points_per_update(w)
