@@ -1,9 +1,10 @@
-"""Import the read-only reference (`/root/reference`, lz1oceani/pointcloud_rl `pyrl`) for golden-vector generation.
+"""Import the unmodified reference (lz1oceani/pointcloud_rl `pyrl`): from the read-only mount `/root/reference` in the
+build container, else from the staged copy `oracle/_ref/` (oracle/build_ref.py; git-ignored, travels to the GPU box).
 
-TEST INFRASTRUCTURE ONLY.  Nothing in `pointcloud_rl_b200/` imports this module.  The reference is a
-Python package that cannot travel to the GPU box, so this loader is only usable in the build container;
-`tests/golden/make_golden.py` uses it to run the reference's own SAC/DrQ/PointNet code on seeded inputs
-and commits the results as fixtures that pin `oracle/pointnet_sac_oracle.py`.
+TEST / BENCH INFRASTRUCTURE ONLY.  Nothing in `pointcloud_rl_b200/` imports this module.
+`tests/golden/make_golden.py` uses it to run the reference's own SAC/DrQ/PointNet code on seeded inputs and commits
+the results as fixtures that pin `oracle/pointnet_sac_oracle.py`; `bench.py` uses it for the reference arm
+(`--impl reference`, `cpu_baseline.kind = "reference"`) and the reference-on-torch-CUDA comparator.
 
 Only stubs for absent third-party packages are provided (oracle/refshim); no reference source is
 copied or modified.  Recipe follows SURVEY.md Appendix A.
@@ -11,8 +12,18 @@ copied or modified.  Recipe follows SURVEY.md Appendix A.
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("PCRL_REFERENCE_ROOT", "/root/reference")
-_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "refshim")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIM = os.path.join(_HERE, "refshim")
+
+
+def _find_root():
+    for cand in (os.environ.get("PCRL_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "pyrl")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available():
@@ -22,7 +33,8 @@ def reference_available():
 def load_reference():
     """Returns a namespace of the reference symbols the golden generator needs."""
     if not reference_available():
-        raise RuntimeError(f"reference not found at {REFERENCE_ROOT}; golden vectors can only be regenerated in the build container")
+        raise RuntimeError(f"reference not found at {REFERENCE_ROOT} (nor staged under oracle/_ref: run oracle/build_ref.py "
+                           "in the build container)")
     os.environ.setdefault("PYTHONDONTWRITEBYTECODE", "1")
     sys.dont_write_bytecode = True
     for p in (_SHIM, REFERENCE_ROOT):

@@ -37,9 +37,19 @@ class FlatAdam:
     `param_groups`, `state_dict()` / `load_state_dict()` in torch.optim.Adam's layout (one group per tensor,
     as build_optimizer does, optimizer_utils.py:31-64) so reference checkpoints round-trip."""
 
-    def __init__(self, agent, group, step_index, lr, betas, names):
+    SUPPORTED = {"type", "lr", "betas", "eps", "weight_decay", "amsgrad", "param_cfg", "constructor"}
+
+    def __init__(self, agent, group, step_index, optim_cfg, names):
         self.agent, self.group, self.step_index, self.names = agent, group, step_index, names
-        self.defaults = dict(lr=lr, betas=tuple(betas), eps=1e-8, weight_decay=0, amsgrad=False)
+        cfg = dict(optim_cfg)
+        unknown = set(cfg) - self.SUPPORTED
+        if unknown:
+            raise NotImplementedError(f"optimizer options {sorted(unknown)} are not implemented by the fused Adam")
+        if cfg.get("type", "Adam") != "Adam" or cfg.get("weight_decay", 0) != 0 or cfg.get("amsgrad", False):
+            raise NotImplementedError("the fused optimizer is plain Adam (no weight decay, no amsgrad): "
+                                      "optimizer_utils.py:31-64 with the pn_base.py settings")
+        self.defaults = dict(lr=float(cfg.get("lr", 1e-3)), betas=tuple(cfg.get("betas", (0.9, 0.999))),
+                             eps=float(cfg.get("eps", 1e-8)), weight_decay=0, amsgrad=False)
 
     @property
     def param_groups(self):
@@ -60,6 +70,14 @@ class FlatAdam:
 
     def load_state_dict(self, sd):
         eng = self.agent._ensure_engine()
+        for grp in sd.get("param_groups", []):
+            # the fused kernel has ONE hyper-parameter set per optimizer: a checkpoint whose groups disagree with the
+            # configured values would silently train differently
+            for key in ("lr", "betas", "eps"):
+                if key in grp and tuple(np.atleast_1d(grp[key]).tolist()) != tuple(np.atleast_1d(self.defaults[key]).tolist()):
+                    raise ValueError(f"checkpoint optimizer {key}={grp[key]} differs from the configured {self.defaults[key]}")
+            if grp.get("weight_decay", 0) != 0 or grp.get("amsgrad", False):
+                raise NotImplementedError("checkpoint optimizer uses weight decay / amsgrad")
         m, v = eng.layout.views(eng.adam_m), eng.layout.views(eng.adam_v)
         steps = set()
         for i, n in enumerate(self.names):
@@ -104,8 +122,22 @@ class BaseAgent(ExtendedModule):
 
         self._device_ids = device_ids
         self._be_data_parallel = True
-        if dist.is_initialized():
-            attach(self._ensure_engine())
+        if dist.is_initialized() and self.engine is not None:
+            self._attach_ddp(self.engine)
+        # otherwise _ensure_engine() attaches as soon as the engine exists (it needs a first batch for its shapes)
+
+    def _attach_ddp(self, eng):
+        """What wrapping in DDP does at wrap time (module_utils.py:322-337): every rank starts from rank 0's
+        parameters / targets / optimizer state; plus the gradient all-reduce and a per-rank random stream."""
+        import torch.distributed as dist
+
+        from .dist import attach, broadcast_state
+
+        if not dist.is_initialized():
+            raise RuntimeError("to_ddp() needs torch.distributed to be initialised (one process per GPU)")
+        attach(eng)
+        broadcast_state(eng)
+        eng.seed = int(self.seed) + dist.get_rank()  # augmentation / policy noise must differ between ranks
 
     def to_normal(self):
         self._be_data_parallel = False
@@ -149,9 +181,6 @@ class SAC(BaseAgent):
         actor_cfg, critic_cfg = copy.deepcopy([actor_cfg, critic_cfg])
         self._actor_optim_cfg, self._critic_optim_cfg = actor_cfg.pop("optim_cfg"), critic_cfg.pop("optim_cfg")
         self._alpha_optim_cfg = alpha_optim_cfg or dict(type="Adam", lr=1e-3)
-        for cfg in (self._actor_optim_cfg, self._critic_optim_cfg, self._alpha_optim_cfg):
-            if cfg.get("type", "Adam") != "Adam":
-                raise NotImplementedError("only Adam optimizers are fused")
         pc = self._actor_optim_cfg.get("param_cfg") or {}
         if not any(v is None and re.search(pat, "backbone.visual_nn.x") for pat, v in pc.items()):
             raise NotImplementedError("the actor optimizer must exclude visual_nn (param_cfg={'(.*?)visual_nn(.*?)': None})")
@@ -161,6 +190,10 @@ class SAC(BaseAgent):
         self.actor, self.critic = build_actor_critic(actor_cfg, critic_cfg, shared_backbone)
         self.actor.backbone.visual_nn.precision = precision  # rollout-path encodes use the agent's precision
         shared_target = shared_backbone if shared_target_backbone is None else shared_target_backbone
+        if not shared_target:
+            raise NotImplementedError("shared_target_backbone=False (a separate, Polyak-averaged target PointNet) is not "
+                                      "implemented: the engine encodes next_obs with the live PointNet (builder.py:28-45 "
+                                      "with the pn.py configs, where the target shares it)")
         self.target_critic = build_target_network(critic_cfg, self.critic, self.actor, shared_target)
 
         self.log_alpha = nn.Parameter(torch.ones(1) * float(np.log(np.float32(alpha))))
@@ -172,13 +205,13 @@ class SAC(BaseAgent):
 
         names_pn = ["pn.w0", "pn.b0", "pn.w1", "pn.g1", "pn.be1", "pn.w2", "pn.g2", "pn.be2", "pn.wf", "pn.bf", "pn.gf", "pn.bef"]
         mk = ["w0", "b0", "w1", "b1", "w2", "b2"]
-        self.actor_optim = FlatAdam(self, "actor", 1, self._actor_optim_cfg.get("lr", 1e-3),
-                                    self._actor_optim_cfg.get("betas", (0.9, 0.999)), [f"actor.{k}" for k in mk])
-        self.critic_optim = FlatAdam(self, "critic", 0, self._critic_optim_cfg.get("lr", 1e-3),
-                                     self._critic_optim_cfg.get("betas", (0.9, 0.999)),
+        self.actor_optim = FlatAdam(self, "actor", 1, self._actor_optim_cfg, [f"actor.{k}" for k in mk])
+        self.critic_optim = FlatAdam(self, "critic", 0, self._critic_optim_cfg,
                                      names_pn + [f"q0.{k}" for k in mk] + [f"q1.{k}" for k in mk])
-        self.alpha_optim = FlatAdam(self, "alpha", 2, self._alpha_optim_cfg.get("lr", 1e-3),
-                                    self._alpha_optim_cfg.get("betas", (0.9, 0.999)), ["log_alpha"])
+        self.alpha_optim = FlatAdam(self, "alpha", 2, self._alpha_optim_cfg, ["log_alpha"])
+        eps = {o.defaults["eps"] for o in (self.actor_optim, self.critic_optim, self.alpha_optim)}
+        if len(eps) != 1:
+            raise NotImplementedError("the three optimizers must share one Adam eps")
         self._aug = None
         self._num_aug = 1
 
@@ -202,7 +235,8 @@ class SAC(BaseAgent):
             aug=kind, aug_lo=lo, aug_hi=hi, aug_axes=axes, tau=self._tau, actor_update_interval=self.actor_update_interval,
             target_update_interval=self.target_update_interval, lr=self.critic_optim.defaults["lr"],
             actor_lr=self.actor_optim.defaults["lr"], alpha_lr=self.alpha_optim.defaults["lr"],
-            betas=self.critic_optim.defaults["betas"], alpha_betas=self.alpha_optim.defaults["betas"],
+            betas=self.critic_optim.defaults["betas"], actor_betas=self.actor_optim.defaults["betas"], alpha_betas=self.alpha_optim.defaults["betas"],
+            adam_eps=self.critic_optim.defaults["eps"],
             log_std_bound=(head.log_std_min, head.log_std_max), head_scale=head.scale_value, head_bias=head.bias_value,
             target_entropy=float(self.target_entropy), ignore_dones=self.ignore_dones,
             automatic_alpha_tuning=self.automatic_alpha_tuning)
@@ -241,6 +275,8 @@ class SAC(BaseAgent):
             mod_prm.data = eng.p[name].view(shape)
         eng.prime_alpha()
         self.engine = eng
+        if self._be_data_parallel:
+            self._attach_ddp(eng)
         return eng
 
     def _module_params(self):

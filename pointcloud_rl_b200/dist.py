@@ -28,3 +28,12 @@ def broadcast_params(engine, src=0, group=None):
     """Make every rank start from rank `src`'s weights (what DDP does at wrap time)."""
     dist.broadcast(engine.params, src=src, group=group)
     engine.refresh_alpha()
+
+
+def broadcast_state(engine, src=0, group=None):
+    """Parameters, target networks, Adam moments and step counters of rank `src` on every rank: the replicas then stay
+    identical because they all apply the same reduced gradient."""
+    for t in (engine.params, engine.adam_m, engine.adam_v, engine.steps):
+        dist.broadcast(t, src=src, group=group)
+    engine.refresh_alpha()
+    engine.prime_alpha()

@@ -102,6 +102,7 @@ class HyperParams:
     actor_lr: float = 1e-3
     alpha_lr: float = 1e-3
     betas: Tuple[float, float] = (0.9, 0.999)
+    actor_betas: Tuple[float, float] = (0.9, 0.999)
     alpha_betas: Tuple[float, float] = (0.5, 0.999)
     adam_eps: float = 1e-8
     log_std_bound: Tuple[float, float] = (-10.0, 2.0)
@@ -253,12 +254,17 @@ class UpdateEngine:
         self.fwd_ws_bytes = int(self.L.pointnet_fwd_f32_workspace(chunk, NP, c1, c2, c3))
         self.bwd_ws_bytes = int(self.L.pointnet_bwd_workspace(R, NP, c1, c2, c3, CP))
         w["scratch"] = torch.zeros(max(self.fwd_ws_bytes, self.bwd_ws_bytes), dtype=torch.uint8, device=dev)
+        if not bf16:
+            # the target branch's encode(next) runs on a forked stream beside encode(obs): it needs its own forward
+            # workspace (the bf16 path keeps its intermediates on chip and has per-branch pool_keys_* buffers)
+            w["scratch_next"] = torch.zeros(self.fwd_ws_bytes, dtype=torch.uint8, device=dev)
         if bf16:
             w["wpack"] = torch.zeros(int(self.L.pointnet_wpack_bytes(c1, c2, c3)), dtype=torch.uint8, device=dev)
             for name in ("next", "obs", "pi"):
                 w[f"pool_keys_{name}"] = torch.zeros(R * c3, dtype=torch.int64, device=dev)
         self.w = w
         self._graphs = {}
+        self._noise_static = {}
         self.graph_calls = {}
         # side streams 0-2 carry branches of the critical chain (target branch, second Q head): high priority, like the
         # capture stream; 3-8 carry the weight-gradient GEMMs that only feed the optimizer: default (low) priority, so
@@ -284,20 +290,47 @@ class UpdateEngine:
         return {k: v.detach().clone().cpu() for k, v in self.p.items()}
 
     def refresh_alpha(self):
-        self.L.refresh_alpha(self.p["log_alpha"], self.alpha_dev, self.scalars, stream_ptr())
+        with torch.cuda.device(self.device):
+            self.L.refresh_alpha(self.p["log_alpha"], self.alpha_dev, self.scalars, stream_ptr())
 
     # ------------------------------------------------------------------ batch upload (host -> device)
     def upload_batch(self, batch):
         """batch: dict(obs, next_obs, actions, rewards, dones) of numpy arrays / torch CPU tensors (the
-        reference's `memory.sample(B)` layout, replay_buffer.py:297-322).  Host->device copies go through
-        pinned staging buffers so they are asynchronous on the current stream."""
+        reference's `memory.sample(B)` layout, replay_buffer.py:297-322).  Every leaf is copied into its slot of ONE
+        pinned staging buffer and its host->device copy is enqueued at once, so the DMA of leaf i overlaps the host
+        memcpy of leaf i+1; two staging buffers alternate so a call never overwrites bytes a previous call's DMA
+        may still be reading."""
         if self._pinned is None:
-            self._pinned = torch.empty(self._batch_bytes, dtype=torch.uint8).pin_memory()
-            self._pinned_views = self._batch_views(self._pinned)
-        for key, src in self._flatten_batch(batch).items():
-            self._pinned_views[key].copy_(src)
-        self.raw_flat.copy_(self._pinned, non_blocking=True)
+            self._pinned = [torch.empty(self._batch_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+            self._pinned_np = [{k: v.numpy() for k, v in self._batch_views(p).items()} for p in self._pinned]
+            self._pinned_ev = [None, None]
+            self._pinned_i = 0
+        i = self._pinned_i = self._pinned_i ^ 1
+        if self._pinned_ev[i] is not None:
+            self._pinned_ev[i].synchronize()
+        host, views = self._pinned[i], self._pinned_np[i]
+        with torch.cuda.device(self.device):
+            for key, _shape, _dt, off, nbytes in self._batch_layout:
+                src = self._host_leaf(batch, key)
+                dst = views[key]
+                np.copyto(dst, src.reshape(dst.shape), casting="unsafe")  # bool -> u8, f64 -> f32 where needed
+                self.raw_flat[off:off + nbytes].copy_(host[off:off + nbytes], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._pinned_ev[i] = ev
         return sum(n for *_, n in self._batch_layout)
+
+    @staticmethod
+    def _host_leaf(batch, key):
+        if "/" in key:
+            which, leaf = key.split("/")
+            obs = batch[which]
+            v = obs[leaf] if leaf in obs else obs["agent" if leaf == "state" else leaf]
+        else:
+            v = batch[key]
+        if torch.is_tensor(v):
+            v = v.detach().cpu().numpy()
+        return np.asarray(v)
 
     def _batch_views(self, flat):
         """Typed leaf views (flattened keys) into a byte buffer laid out like `raw_flat`."""
@@ -343,6 +376,19 @@ class UpdateEngine:
         writes the feature into cat_<name>[:, :D]."""
         sp, w, p = self.spec, self.w, self.p
         c1, c2, c3 = sp.widths
+        self._encode_points(name, rows, want_argmax, st)
+        D = sp.out_dim
+        cat = w[f"cat_{name}"]
+        self.L.linear_fwd(w[f"pooled_{name}"], c3, p["pn.wf"], p["pn.bf"], w[f"z_{name}"], D, rows, c3, D, 0, self.tf32, st)
+        save = want_argmax
+        self.L.layernorm_fwd(w[f"z_{name}"], p["pn.gf"], p["pn.bef"], cat, cat.stride(0),
+                             w["xhat_obs"] if save else None, w["rstd_obs"] if save else None, rows, D,
+                             sp.head_ln_eps, st)
+
+    def _encode_points(self, name, rows, want_argmax, st):
+        """The fused per-point MLP + LayerNorm + ReLU + max-pool (+argmax) kernel: staged points -> pooled_<name>."""
+        sp, w, p = self.spec, self.w, self.p
+        c1, c2, c3 = sp.widths
         argmax = w["argmax_obs"] if want_argmax else None
         if self.precision == "bf16":
             if name == "pi" and self.k > 1:  # first augmentation of every sample, read in place from the obs staging
@@ -354,14 +400,11 @@ class UpdateEngine:
         else:
             self.L.pointnet_fwd_f32(w[f"xf_{name}"], rows, sp.n_points, sp.NP, sp.CP, sp.C, p["pn.w0"], p["pn.b0"],
                                     p["pn.w1"], p["pn.g1"], p["pn.be1"], p["pn.w2"], p["pn.g2"], p["pn.be2"], c1, c2,
-                                    c3, sp.ln_eps, w[f"pooled_{name}"], argmax, w["scratch"], self.fwd_ws_bytes, st)
-        D = sp.out_dim
-        cat = w[f"cat_{name}"]
-        self.L.linear_fwd(w[f"pooled_{name}"], c3, p["pn.wf"], p["pn.bf"], w[f"z_{name}"], D, rows, c3, D, 0, self.tf32, st)
-        save = want_argmax
-        self.L.layernorm_fwd(w[f"z_{name}"], p["pn.gf"], p["pn.bef"], cat, cat.stride(0),
-                             w["xhat_obs"] if save else None, w["rstd_obs"] if save else None, rows, D,
-                             sp.head_ln_eps, st)
+                                    c3, sp.ln_eps, w[f"pooled_{name}"], argmax,
+                                    w["scratch_next" if name == "next" else "scratch"], self.fwd_ws_bytes, st)
+
+    def dominant_kernel_name(self):
+        return "pointnet_fwd_tc_kernel" if self.precision == "bf16" else "pointnet_fwd_f32 chain"
 
     def _pack_weights(self, st):
         """bf16 path: re-pack the (just updated) PointNet weights into the MMA-ready smem image."""
@@ -472,8 +515,13 @@ class UpdateEngine:
             cur.wait_stream(s_)
 
     def update(self, updates: int, noise: Optional[Dict[str, torch.Tensor]] = None):
-        """Enqueues one full update on the current stream.  `noise` (parity mode) injects the reference's
-        random draws: jitter_obs/jitter_next, angle_obs/angle_next or shift_obs/shift_next, eps_next, eps_pi (device tensors)."""
+        """Enqueues one full update on the current stream of the engine's device.  `noise` (parity mode) injects the
+        reference's random draws: jitter_obs/jitter_next, angle_obs/angle_next or shift_obs/shift_next, eps_next, eps_pi
+        (device tensors)."""
+        with torch.cuda.device(self.device):  # kernels launch on the CURRENT device: pin it to the engine's
+            self._update(updates, noise)
+
+    def _update(self, updates, noise):
         sp, hp, w, p, L = self.spec, self.hp, self.w, self.p, self.L
         ST = stream_ptr  # evaluated at every call site: forked sections run on their own stream
         B, R, k = self.B, self.R, self.k
@@ -492,9 +540,8 @@ class UpdateEngine:
                 m = w[f"ds_map_{which}"]
                 keep = noise.get(f"keep_{which}")
                 if keep is not None:
-                    keep = keep.to(device=m.device, dtype=torch.int64)
-                    m.fill_(int(keep[0]))
-                    m[keep] = keep.to(torch.int32)
+                    if not torch.cuda.is_current_stream_capturing():  # graphs: update_graphed() built the map already
+                        self._set_downsample_map(m, keep)
                 else:
                     L.downsample_map(sp.n_points, float(hp.aug_lo), int(hp.aug_hi != 0), self.seed, self.counter, sid, m, ST())
                 maps[f"keep_{which}"] = m
@@ -629,18 +676,42 @@ class UpdateEngine:
             if self.allreduce is not None:
                 al_lo, al_hi = self.layout.group_range["alpha"]
                 self.allreduce(self.grads[a_lo:al_hi])  # actor grads | d log_alpha in one message
-            self._adam("actor", 1, hp.actor_lr, hp.betas, 8, False, ST())
+            self._adam("actor", 1, hp.actor_lr, hp.actor_betas, 8, False, ST())
             if hp.automatic_alpha_tuning:
                 self._adam("alpha", 2, hp.alpha_lr, hp.alpha_betas, None, False, ST())
                 self.refresh_alpha()
         self.counter.add_(1)
 
+    @staticmethod
+    def _set_downsample_map(m, keep):
+        """Source map of RandomDownSample from the injected kept indices: dropped points read the first kept one."""
+        keep = keep.to(device=m.device, dtype=torch.int64)
+        m.copy_(keep[:1].to(torch.int32).expand_as(m))
+        m[keep] = keep.to(torch.int32)
+
     # ------------------------------------------------------------------ CUDA graphs
-    def update_graphed(self, updates: int):
-        """Same as update() (Philox randomness only) but replayed from a CUDA graph: one launch per update
-        instead of ~150.  Two graphs exist at most per (actor step?, target step?) combination."""
+    def update_graphed(self, updates: int, noise: Optional[Dict[str, torch.Tensor]] = None):
+        """Same as update() but replayed from a CUDA graph: one launch per update instead of ~150.  Two graphs exist at
+        most per (actor step?, target step?) combination.  `noise` (parity mode) is copied into static device buffers
+        the captured kernels read, so the graph path can be compared with the reference draw for draw."""
+        with torch.cuda.device(self.device):
+            return self._update_graphed(updates, noise)
+
+    def _update_graphed(self, updates, noise):
         hp = self.hp
-        key = (updates % hp.actor_update_interval == 0, updates % hp.target_update_interval == 0)
+        key = (updates % hp.actor_update_interval == 0, updates % hp.target_update_interval == 0,
+               tuple(sorted(noise)) if noise else None)
+        static = None
+        if noise:
+            static = self._noise_static.setdefault(key, {})
+            for k_, v in noise.items():
+                if k_.startswith("keep_"):  # variable-length index list: turned into the fixed-size source map here
+                    self._set_downsample_map(self.w[f"ds_map_{k_[5:]}"], v)
+                    static[k_] = v
+                    continue
+                if k_ not in static:
+                    static[k_] = torch.empty_like(v, device=self.device)
+                static[k_].copy_(v, non_blocking=True)
         g = self._graphs.get(key)
         if g is None:
             # warm-up outside capture (module loading, cudaFuncSetAttribute), on a side stream as torch requires
@@ -649,7 +720,7 @@ class UpdateEngine:
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                self.update(updates)
+                self._update(updates, static)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize(self.device)
             for dst, src in zip((self.params, self.adam_m, self.adam_v, self.steps, self.counter, self.alpha_dev,
@@ -658,12 +729,21 @@ class UpdateEngine:
             g = torch.cuda.CUDAGraph()
             n0 = self.L.launches
             with torch.cuda.graph(g, stream=self._capture_stream):
-                self.update(updates)
+                self._update(updates, static)
             self.graph_calls[key] = self.L.launches - n0  # C-ABI calls (>= 1 kernel each) replayed per launch
             # capture does not execute: state is untouched
             self._graphs[key] = g
         g.replay()
         return self.graph_calls[key]
+
+    def close(self):
+        """Drops the captured CUDA graphs (they hold NCCL kernels when a gradient all-reduce is attached: destroy them
+        BEFORE the process group, or communicator teardown blocks)."""
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            self._graphs.clear()
+            self._noise_static.clear()
+            torch.cuda.synchronize(self.device)
 
     # ------------------------------------------------------------------ pipelined host->device input path
     def make_pinned_batch(self, batch):
@@ -715,9 +795,10 @@ class UpdateEngine:
     def read_scalars(self, updates: int, sync=True):
         """One device->host copy of everything update_parameters() logs (vs ~11 .item() syncs, sac.py:140-203)."""
         if self.scalars_host is not None:
-            self.scalars_host.copy_(self.scalars, non_blocking=True)
-            if sync:
-                torch.cuda.current_stream().synchronize()
+            with torch.cuda.device(self.device):
+                self.scalars_host.copy_(self.scalars, non_blocking=True)
+                if sync:
+                    torch.cuda.current_stream().synchronize()
             s = self.scalars_host.numpy().astype(np.float64)
         else:
             s = self.scalars.cpu().numpy().astype(np.float64)

@@ -161,6 +161,7 @@ class KernelRunner:
         self.precision = precision
         self.tf32 = 1 if precision == "bf16" else 0
         self.seed = seed
+        self.L = lib()
         self._ws = {}
         self._counter = None
         self.calls = 0

@@ -63,3 +63,36 @@ def init_params(seed, spec, zero_out_logstd=False, alpha=0.1):
         p["actor.b2"][A:] = (torch.rand(A, generator=g) * 2 - 1) * 1e-3
     p["log_alpha"] = torch.ones(1) * float(np.log(np.float32(alpha)))
     return p
+
+
+class SimpleBox:
+    """gym.spaces.Box stand-in: the actor head only reads low / high / is_bounded() (actor_critic.py:69-71)."""
+
+    def __init__(self, low, high, shape):
+        self.low, self.high, self.shape = np.full(shape, low, np.float32), np.full(shape, high, np.float32), tuple(shape)
+
+    def is_bounded(self):
+        return True
+
+
+def obs_shape_of(obs):
+    """env_params['obs_shape'] of a batched observation dict (dict_array.py:364-374: lists for >= 2-D leaves, ints for 1-D)."""
+    return {k: (list(v.shape[1:]) if np.ndim(v) > 2 else int(np.shape(v)[1])) for k, v in obs.items()}
+
+
+def make_agent(config_rel, obs_shape, action_dim, overrides=None, **agent_kwargs):
+    """Agent from one of the packaged config files, built exactly like run_rl.py builds the reference's
+    (Config.fromfile -> env_params -> replace_placeholder_with_args -> build_agent; run_rl.py:505-543).
+    `overrides`: dotted keys under agent_cfg (e.g. {"actor_cfg.nn_cfg.mlp_cfg.mlp_spec": [...]}); `agent_kwargs`:
+    top-level agent options (batch_size, precision, use_cuda_graph, seed, ...)."""
+    from . import Config, config_path, get_kwargs_from_shape, replace_placeholder_with_args
+    from .agents import build_agent
+
+    cfg = Config.fromfile(config_path(config_rel))
+    merged = {f"agent_cfg.{k}": v for k, v in {**(overrides or {}), **agent_kwargs}.items()}
+    if merged:
+        cfg.merge_from_dict(merged)
+    cfg.agent_cfg["env_params"] = dict(obs_shape=obs_shape, action_shape=action_dim,
+                                       action_space=SimpleBox(-1.0, 1.0, (action_dim,)), is_discrete=False)
+    cfg = replace_placeholder_with_args(cfg, **get_kwargs_from_shape(obs_shape, action_dim))
+    return build_agent(cfg.agent_cfg)

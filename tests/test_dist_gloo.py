@@ -14,16 +14,22 @@ class _FakeEngine:
         self.world_size = 1
         self.allreduce = None
         self.params = torch.zeros(8)
+        self.adam_m, self.adam_v = torch.zeros(8), torch.zeros(8)
+        self.steps = torch.zeros(4, dtype=torch.int32)
+        self.primed = 0
 
     def refresh_alpha(self):
         pass
+
+    def prime_alpha(self):
+        self.primed += 1
 
 
 def _worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from pointcloud_rl_b200.dist import attach, broadcast_params
+    from pointcloud_rl_b200.dist import attach, broadcast_params, broadcast_state
 
     eng = attach(_FakeEngine())
     assert eng.world_size == world and eng.allreduce is not None
@@ -38,6 +44,14 @@ def _worker(rank, world, port, out):
     eng.params = torch.full((8,), float(rank + 1))
     broadcast_params(eng, src=0)
     ok = ok and bool((eng.params == 1.0).all())
+    # to_ddp(): parameters, Adam moments and step counters all follow rank 0 (what DDP wrapping does for the weights)
+    eng.params = torch.full((8,), float(rank + 3))
+    eng.adam_m = torch.full((8,), float(rank + 5))
+    eng.adam_v = torch.full((8,), float(rank + 7))
+    eng.steps = torch.full((4,), rank + 2, dtype=torch.int32)
+    broadcast_state(eng, src=0)
+    ok = ok and bool((eng.params == 3.0).all() and (eng.adam_m == 5.0).all() and (eng.adam_v == 7.0).all())
+    ok = ok and bool((eng.steps == 2).all()) and eng.primed == 1
     if rank == 0:
         out.put(ok)
     dist.barrier()
