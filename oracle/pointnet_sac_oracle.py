@@ -119,11 +119,20 @@ def pointnet_point_features(p, x, ln_eps=1e-6):
     return h
 
 
-def pointnet_forward(p, x, ln_eps=1e-6, return_pool=False):
+def pointnet_forward(p, x, ln_eps=1e-6, return_pool=False, idx_override=None):
     """PointNet.forward, pointnet.py:112-157 with feature_transform=[]: per-point MLP, max over
-    points (ties -> smallest index, torch semantics), Linear + LayerNorm(eps=1e-5) (pointnet.py:110)."""
+    points (ties -> smallest index, torch semantics), Linear + LayerNorm(eps=1e-5) (pointnet.py:110).
+
+    idx_override [B,c3] (tests of the reduced-precision tier only): pool the points a kernel selected instead of
+    the fp32 argmax.  max-pool routes each channel's gradient to ONE point, so a near-tie resolved differently under
+    bf16 rounding moves that channel's whole gradient; with the selection pinned, the remaining difference is
+    arithmetic error, which is what the tolerance is about (the selection itself is checked by the near-tie rule)."""
     h = pointnet_point_features(p, x, ln_eps)
-    pooled, idx = h.max(dim=-1)
+    if idx_override is None:
+        pooled, idx = h.max(dim=-1)
+    else:
+        idx = idx_override.long()
+        pooled = torch.gather(h, 2, idx[..., None])[..., 0]
     z = pooled @ p["pn.wf"].t() + p["pn.bf"]
     out = F.layer_norm(z, (z.shape[-1],), p["pn.gf"], p["pn.bef"], 1e-5)
     if return_pool:
@@ -297,7 +306,7 @@ def _cat(*xs):
     return torch.cat([x for x in xs if x is not None], dim=-1)
 
 
-def update(state, batch, updates, hp, noise, capture=None):
+def update(state, batch, updates, hp, noise, capture=None, idx_override=None):
     """One SAC / DrQ `update_parameters(memory, updates)` on an already-sampled batch.
 
     batch: dict(obs=dict, next_obs=dict, actions [B,A], rewards [B,1], dones [B,1]) of numpy / torch.
@@ -357,12 +366,15 @@ def update(state, batch, updates, hp, noise, capture=None):
     # ---- critic step: sac.py:136-148 / drq.py:89-101
     ck = critic_keys()
     leaves = {name: p[name].detach().clone().requires_grad_(True) for name in ck}
-    f, pooled, idx = pointnet_forward(leaves, x_obs, return_pool=True)
+    f, pooled, idx = pointnet_forward(leaves, x_obs, return_pool=True, idx_override=idx_override)
     q_in = _cat(f, robot, actions_k)
     q = torch.cat([mlp3(leaves, "q0", q_in), mlp3(leaves, "q1", q_in)], dim=-1)
     critic_loss = F.mse_loss(q, q_target) * 2
     grads = torch.autograd.grad(critic_loss, [leaves[name] for name in ck])
     cap.update(f_obs=f.detach(), pooled_obs=pooled.detach(), idx_obs=idx, q=q.detach(), critic_grads=dict(zip(ck, grads)))
+    if idx_override is not None:  # every candidate's true post-ReLU feature, for the near-tie check of the selection
+        with torch.no_grad():
+            cap["h_obs_max"] = pointnet_point_features(p, x_obs).max(dim=-1)[0]
     ret = {
         f"{pre}/critic_loss": float(critic_loss.item()),
         f"{pre}/max_critic_abs_err": float((q - q_target).abs().max().item()),

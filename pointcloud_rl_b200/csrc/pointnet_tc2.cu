@@ -1,0 +1,573 @@
+// Fused PointNet per-point MLP + max-pool on tcgen05 / TMEM, second generation (sm_100a).
+//
+// What bounded the first kernel (pointnet_tc.cu) was not the tensor pipe but the layer-2 epilogue: with points on the
+// TMEM lanes, LayerNorm is thread-local but the max over points is the CROSS-lane direction, i.e. a transpose of every
+// accumulator element through shared memory (256 KB of shared-memory traffic and ~3 instructions per element).
+// Here layer 2 is issued TRANSPOSED,  D[channel, point] = W2 . h1^T  (channels on the TMEM lanes, points on the
+// columns), so the max over points is a thread-local running maximum over the accumulator row -- no shuffles, no
+// shared memory -- and LayerNorm's statistics, which would now be the cross-lane direction, never touch the
+// accumulator at all:
+//   * mean:      W1 and W2 are packed CENTRED over their output channels (W[c,:] - mean_c W[c,:]), so every
+//                accumulator already holds y - mean(y);
+//   * variance:  sum_c (y_c - mean)^2 = h1^T Gc h1 with the Gram matrix Gc = W2c^T W2c (c2 x c2, packed once per
+//                weight update): one extra N = c2 MMA per tile, U = h1 . Gc, and a thread-local dot(h1, U) in the
+//                warp that produced h1 (points on lanes there).
+// The layer-2 epilogue is then  z = y * rstd[point]  (sign(gamma2) folded into the packed weights as before, so
+// |gamma2|, beta2 and the ReLU commute with the max and run once per (cloud, channel) in the finalize kernel) and a
+// 3-input max: ~1.25 instructions per accumulator element instead of ~4.5, and no shared-memory traffic.
+//
+// Per 128-point tile (c = (c1, c2, c3)):
+//   acc0 = X W0'^T                 (M = points, K = 16)      -> relu            -> h0 (bf16, smem)
+//   acc1 = h0 W1c^T                (M = points, N = c2)      -> LN + relu       -> h1 (bf16, smem; packed copy in regs)
+//   U    = h1 Gc                   (M = points, N = c2)      -> rstd2 = rsqrt(dot(h1, U) / c3 + eps) -> smem
+//   D_b  = W2c'[128 b .. ] h1^T    (M = channels, N = points) for b < c3 / 128  -> * rstd2[point] -> running max
+//
+// Persistent, one CTA per SM, 16 warps:
+//   warp 0      bulk-TMA producer (weights once; 4 KB point tiles through a 3-stage ring)
+//   warp 1, 2   MMA issuers of tile slots 0 / 1 (layers 0, 1 and the Gram MMA; odd and even tiles ping-pong)
+//   warp 3      MMA issuer of the transposed layer 2
+//   warps 4-7   front group of slot 0 (one warp per TMEM lane quadrant, a thread owns a whole point row)
+//   warps 8-11  front group of slot 1
+//   warps 12-15 pool group (a thread owns one channel of every 128-channel block)
+// TMEM (512 columns): [0,128) slot 0 and [128,256) slot 1 (acc0 / acc1 / U alias: each is drained before the next MMA
+// overwrites it), [256,384) and [384,512) the two transposed layer-2 accumulators (one per 128-channel block, ring).
+#include <algorithm>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "pointnet_tc2.cuh"
+#include "tc_ptx.cuh"
+
+namespace pcrl {
+namespace tc2 {
+using namespace pcrl::tc;
+
+constexpr int kStages = 3;
+constexpr int kTileBytes = 128 * 16 * 2;  // one X tile: 128 points x 16 bf16
+constexpr int kThreads = 512;
+
+// Packed weight buffer, second generation (appended to the first generation's buffer, which the backward's dump mode
+// still reads):  [ W0' | W1c | Gc | W2c' | g1 be1 ]  <- one contiguous shared-memory image;  [ g2 be2 ] for the finalize
+struct Wpack2 {
+  uint32_t w0, w1, gc, w2, prm1, img_bytes, prm2, total;
+};
+__host__ __device__ inline Wpack2 make_wpack2(int c1, int c2, int c3) {
+  Wpack2 W;
+  uint32_t o = 0;
+  W.w0 = o;   o += c1 * 32;
+  W.w1 = o;   o += c2 * c1 * 2;
+  W.gc = o;   o += c2 * c2 * 2;
+  W.w2 = o;   o += c3 * c2 * 2;
+  W.prm1 = o; o += 2 * c2 * 4;
+  W.img_bytes = o;
+  W.prm2 = o; o += 2 * c3 * 4;
+  W.total = (o + 127) & ~127u;
+  return W;
+}
+
+struct Smem2 {
+  uint32_t img, xst, act, rbuf, bars, total;
+};
+__host__ __device__ inline Smem2 make_smem2(int c1, int c2, int c3) {
+  Smem2 L;
+  uint32_t o = 0;
+  L.img = o;  o += make_wpack2(c1, c2, c3).img_bytes;
+  o = (o + 127) & ~127u;
+  L.xst = o;  o += kStages * kTileBytes;
+  L.act = o;  o += 2 * 128 * (c1 > c2 ? c1 : c2) * 2;  // one h0/h1 buffer per tile slot
+  L.rbuf = o; o += 4 * 128 * 4;                        // rstd2 of the last four tiles
+  L.bars = o; o += 256;
+  L.total = o;
+  return L;
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+template <int C1, int C2, int NBLK, bool ARGMAX>
+__global__ void __launch_bounds__(kThreads, 1)
+pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wpack, int n_tiles, int tiles_per_cloud,
+                        int src_cloud_stride, float ln_eps, float key_bias, unsigned long long* __restrict__ pool_keys) {
+  constexpr int C3 = NBLK * 128;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const Smem2 L = make_smem2(C1, C2, C3);
+  const Wpack2 W = make_wpack2(C1, C2, C3);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kActBytes = 128 * (C1 > C2 ? C1 : C2) * 2;
+
+  // mbarriers
+  constexpr int WB = 0;             // weights landed
+  constexpr int XF = 1;             // [kStages] x tile landed
+  constexpr int XE = XF + kStages;  // [kStages] x stage free
+  constexpr int F0 = XE + kStages;  // [slot] acc0 complete (tcgen05.commit)
+  constexpr int F1 = F0 + 2;        // [slot] acc1 complete
+  constexpr int FU = F1 + 2;        // [slot] U complete
+  constexpr int E0 = FU + 2;        // [slot] h0 written, acc0 drained (128 arrivals)
+  constexpr int E1 = E0 + 2;        // [slot] h1 written, acc1 drained
+  constexpr int EU = E1 + 2;        // [slot] U drained, rstd2 written
+  constexpr int HF = EU + 2;        // [slot] the transposed layer-2 MMAs have finished reading the slot's h1
+  constexpr int F2 = HF + 2;        // [ring] transposed layer-2 accumulator complete
+  constexpr int D2 = F2 + 2;        // [ring] ... drained by the pool group (128 arrivals)
+  constexpr int NBAR = D2 + 2;
+  const uint32_t bar0 = sbase + L.bars;
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L.bars + NBAR * 8);
+
+  if (threadIdx.x == 0) {
+    mbar_init(BAR(WB), 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(BAR(XF + s), 1);
+      mbar_init(BAR(XE + s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(BAR(F0 + s), 1);
+      mbar_init(BAR(F1 + s), 1);
+      mbar_init(BAR(FU + s), 1);
+      mbar_init(BAR(E0 + s), 128);
+      mbar_init(BAR(E1 + s), 128);
+      mbar_init(BAR(EU + s), 128);
+      mbar_init(BAR(HF + s), 1);
+      mbar_init(BAR(F2 + s), 1);
+      mbar_init(BAR(D2 + s), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(
+        smem_u32((const void*)tmem_ptr_smem)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // every CTA takes a contiguous range of tiles (consecutive tiles belong to the same cloud)
+  const int t_q = n_tiles / (int)gridDim.x, t_r = n_tiles % (int)gridDim.x;
+  const int n_local = t_q + ((int)blockIdx.x < t_r ? 1 : 0);
+  const int64_t tile0 = (int64_t)blockIdx.x * t_q + min((int)blockIdx.x, t_r);
+  const uint32_t s_w0 = sbase + L.img + W.w0, s_w1 = sbase + L.img + W.w1, s_gc = sbase + L.img + W.gc,
+                 s_w2 = sbase + L.img + W.w2;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(BAR(WB), W.img_bytes);
+      for (uint32_t off = 0; off < W.img_bytes; off += 32768u)
+        bulk_g2s(sbase + L.img + off, wpack + off, min(W.img_bytes - off, 32768u), BAR(WB));
+      for (int i = 0; i < n_local; ++i) {
+        const int st = i % kStages;
+        if (i >= kStages) mbar_wait_relaxed(BAR(XE + st), ((i / kStages) - 1) & 1, 64);
+        mbar_expect_tx(BAR(XF + st), kTileBytes);
+        const int64_t tile = tile0 + i;
+        // cloud r reads the tiles of source cloud r * src_cloud_stride (the actor step encodes the first of the
+        // num_aug staged copies of every sample in place)
+        const int64_t src_tile = src_cloud_stride == 1 ? tile
+                                                        : (tile / tiles_per_cloud) * src_cloud_stride * tiles_per_cloud + tile % tiles_per_cloud;
+        bulk_g2s(sbase + L.xst + st * kTileBytes, xh + src_tile * kTileBytes, kTileBytes, BAR(XF + st));
+      }
+    }
+  } else if (warp == 1 || warp == 2) {
+    // ------------------------------------------------------------------ MMA issuer of one tile slot: layer 0, layer 1, Gram
+    if (lane == 0) {
+      const int s = warp - 1;
+      const uint32_t tm = tmem_base + (uint32_t)(s * 128);
+      const uint32_t act = sbase + L.act + (uint32_t)s * kActBytes;
+      const uint32_t id0 = make_idesc(C1), id1 = make_idesc(C2);
+      mbar_wait(BAR(WB), 0);
+      for (int j = s; j < n_local; j += 2) {
+        const int n = j >> 1, st = j % kStages;
+        mbar_wait(BAR(XF + st), (j / kStages) & 1);
+        if (n > 0) mbar_wait(BAR(EU + s), (n - 1) & 1);  // the slot's previous tile has drained U
+        tc_fence_after();
+        mma_bf16(tm, make_desc(sbase + L.xst + st * kTileBytes, 256), make_desc(s_w0, 256), id0, 0);
+        mma_commit(BAR(XE + st));
+        mma_commit(BAR(F0 + s));
+        mbar_wait(BAR(E0 + s), n & 1);  // h0 in shared memory, acc0 drained
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < C1 / 16; ++ks)
+          mma_bf16(tm, make_desc(act + ks * 256, C1 * 16), make_desc(s_w1 + ks * 256, C1 * 16), id1, ks > 0);
+        mma_commit(BAR(F1 + s));
+        mbar_wait(BAR(E1 + s), n & 1);  // h1 in shared memory, acc1 drained
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < C2 / 16; ++ks)
+          mma_bf16(tm, make_desc(act + ks * 256, C2 * 16), make_desc(s_gc + ks * 256, C2 * 16), id1, ks > 0);
+        mma_commit(BAR(FU + s));
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ MMA issuer of the transposed layer 2
+    if (lane == 0) {
+      const uint32_t idT = make_idesc(128);  // N = the tile's 128 points
+      mbar_wait(BAR(WB), 0);
+      for (int j = 0; j < n_local; ++j) {
+        const int s = j & 1, n = j >> 1;
+        const uint32_t act = sbase + L.act + (uint32_t)s * kActBytes;
+        mbar_wait(BAR(E1 + s), n & 1);  // h1 of tile j in shared memory
+#pragma unroll
+        for (int blk = 0; blk < NBLK; ++blk) {
+          const int g = j * NBLK + blk, r = g & 1, k = g >> 1;
+          if (k > 0) mbar_wait(BAR(D2 + r), (k - 1) & 1);  // the pool group drained the ring slot's previous block
+          tc_fence_after();
+          const uint32_t d = tmem_base + 256u + (uint32_t)(r * 128);
+          const uint32_t wa = s_w2 + (uint32_t)blk * 16u * (uint32_t)(C2 * 16);  // rows 128 blk .. of the W2c' image
+#pragma unroll
+          for (int ks = 0; ks < C2 / 16; ++ks)
+            mma_bf16(d, make_desc(wa + ks * 256, C2 * 16), make_desc(act + ks * 256, C2 * 16), idT, ks > 0);
+          mma_commit(BAR(F2 + r));
+        }
+        mma_commit(BAR(HF + s));  // every MMA that reads the slot's h1 buffer has completed when this fires
+      }
+    }
+  } else if (warp < 12) {
+    // ------------------------------------------------------------------ front groups: layer-0 / layer-1 epilogues + variance of layer 2
+    const int s = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t taddr = tmem_base + (uint32_t)(s * 128) + ((uint32_t)(q * 32) << 16);
+    const float* g1 = reinterpret_cast<const float*>(smem + L.img + W.prm1);
+    const float* be1 = g1 + C2;
+    unsigned char* abuf = smem + L.act + (uint32_t)s * kActBytes;
+    unsigned char* dst0 = abuf + (row >> 3) * (uint32_t)(C1 * 16) + (row & 7) * 16;
+    unsigned char* dst1 = abuf + (row >> 3) * (uint32_t)(C2 * 16) + (row & 7) * 16;
+    float* rbuf = reinterpret_cast<float*>(smem + L.rbuf);
+    mbar_wait(BAR(WB), 0);  // LN parameters landed
+    for (int j = s; j < n_local; j += 2) {
+      const int n = j >> 1;
+      uint32_t v[32];
+      // ---- layer 0: ReLU -> bf16 operand of layer 1
+      mbar_wait(BAR(F0 + s), n & 1);
+      if (n > 0) mbar_wait(BAR(HF + s), (n - 1) & 1);  // the previous tile's transposed layer 2 no longer reads the buffer
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < C1; ch += 32) {
+        tmem_ld32(taddr + ch, v);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          uint4 o;
+          o.x = pack_relu_bf16x2(__uint_as_float(v[8 * jj + 0]), __uint_as_float(v[8 * jj + 1]));
+          o.y = pack_relu_bf16x2(__uint_as_float(v[8 * jj + 2]), __uint_as_float(v[8 * jj + 3]));
+          o.z = pack_relu_bf16x2(__uint_as_float(v[8 * jj + 4]), __uint_as_float(v[8 * jj + 5]));
+          o.w = pack_relu_bf16x2(__uint_as_float(v[8 * jj + 6]), __uint_as_float(v[8 * jj + 7]));
+          *reinterpret_cast<uint4*>(dst0 + ((ch >> 3) + jj) * 128) = o;
+        }
+      }
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive(BAR(E0 + s));
+
+      // ---- layer 1: the accumulator holds y - mean(y) (centred weights): variance, normalise, affine, ReLU
+      mbar_wait(BAR(F1 + s), n & 1);
+      tc_fence_after();
+      uint64_t q01 = pk2f(0.f, 0.f), q23 = q01;
+#pragma unroll
+      for (int ch = 0; ch < C2; ch += 32) {
+        tmem_ld32(taddr + ch, v);
+#pragma unroll
+        for (int jj = 0; jj < 32; jj += 4) {
+          const uint64_t y01 = pk2(v[jj], v[jj + 1]), y23 = pk2(v[jj + 2], v[jj + 3]);
+          q01 = fma2(y01, y01, q01);
+          q23 = fma2(y23, y23, q23);
+        }
+      }
+      float rstd1;
+      {
+        uint32_t a, b, c, d;
+        unpk2(q01, a, b);
+        unpk2(q23, c, d);
+        const float sq = (__uint_as_float(a) + __uint_as_float(b)) + (__uint_as_float(c) + __uint_as_float(d));
+        rstd1 = rsqrtf(sq * (1.0f / (float)C2) + ln_eps);
+      }
+      uint32_t hp[C2 / 2];  // this row's h1 as packed bf16 pairs: the Gram dot below needs it again
+      const uint64_t r2 = pk2f(rstd1, rstd1);
+#pragma unroll
+      for (int ch = 0; ch < C2; ch += 32) {
+        tmem_ld32(taddr + ch, v);
+#pragma unroll
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+          const float4 gg = *reinterpret_cast<const float4*>(g1 + ch + j4);
+          const float4 bb = *reinterpret_cast<const float4*>(be1 + ch + j4);
+          const uint64_t zero2 = pk2f(0.f, 0.f);
+          uint32_t x0, x1, x2, x3;
+          unpk2(fma2(fma2(pk2(v[j4], v[j4 + 1]), r2, zero2), pk2f(gg.x, gg.y), pk2f(bb.x, bb.y)), x0, x1);
+          unpk2(fma2(fma2(pk2(v[j4 + 2], v[j4 + 3]), r2, zero2), pk2f(gg.z, gg.w), pk2f(bb.z, bb.w)), x2, x3);
+          hp[(ch + j4) / 2] = pack_relu_bf16x2(__uint_as_float(x0), __uint_as_float(x1));
+          hp[(ch + j4) / 2 + 1] = pack_relu_bf16x2(__uint_as_float(x2), __uint_as_float(x3));
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          *reinterpret_cast<uint4*>(dst1 + ((ch >> 3) + jj) * 128) =
+              make_uint4(hp[ch / 2 + 4 * jj], hp[ch / 2 + 4 * jj + 1], hp[ch / 2 + 4 * jj + 2], hp[ch / 2 + 4 * jj + 3]);
+      }
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive(BAR(E1 + s));
+
+      // ---- variance of layer 2: sum_c (y2_c - mean)^2 = h1 . (Gc h1) = dot(h1, U)
+      mbar_wait(BAR(FU + s), n & 1);
+      tc_fence_after();
+      uint64_t d01 = pk2f(0.f, 0.f), d23 = d01;
+#pragma unroll
+      for (int ch = 0; ch < C2; ch += 32) {
+        tmem_ld32(taddr + ch, v);
+#pragma unroll
+        for (int jj = 0; jj < 32; jj += 4) {
+          const uint32_t p0 = hp[(ch + jj) / 2], p1 = hp[(ch + jj) / 2 + 1];
+          d01 = fma2(pk2(v[jj], v[jj + 1]), pk2(p0 << 16, p0 & 0xffff0000u), d01);
+          d23 = fma2(pk2(v[jj + 2], v[jj + 3]), pk2(p1 << 16, p1 & 0xffff0000u), d23);
+        }
+      }
+      {
+        uint32_t a, b, c, d;
+        unpk2(d01, a, b);
+        unpk2(d23, c, d);
+        const float ss = (__uint_as_float(a) + __uint_as_float(b)) + (__uint_as_float(c) + __uint_as_float(d));
+        rbuf[(j & 3) * 128 + row] = rsqrtf(fmaxf(ss, 0.f) * (1.0f / (float)C3) + ln_eps);
+      }
+      tc_fence_before();
+      mbar_arrive(BAR(EU + s));
+    }
+  } else {
+    // ------------------------------------------------------------------ pool group: scale by rstd2[point], running max over points
+    // thread (q, lane) owns channel 128 b + 32 q + lane of every block b; TMEM lane = channel, column = point
+    const int q = warp & 3;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const float* rbuf = reinterpret_cast<const float*>(smem + L.rbuf);
+    float m[NBLK];                   // values-only: running maximum over the cloud's points
+    unsigned long long run[NBLK];    // argmax: running (key << 32 | ~index)
+#pragma unroll
+    for (int b = 0; b < NBLK; ++b) {
+      m[b] = -3.0e38f;
+      run[b] = 0ull;
+    }
+    int cur_cloud = n_local > 0 ? (int)(tile0 / tiles_per_cloud) : 0;
+    auto flush = [&](int cloud) {
+#pragma unroll
+      for (int b = 0; b < NBLK; ++b) {
+        unsigned long long key;
+        if (ARGMAX) {
+          key = run[b];
+        } else {
+          key = (unsigned long long)(__float_as_uint(m[b] + key_bias) & 0xffffff80u) << 32;  // same bits as the argmax variant
+        }
+        atomicMax(pool_keys + (int64_t)cloud * C3 + b * 128 + q * 32 + lane, key);
+        m[b] = -3.0e38f;
+        run[b] = 0ull;
+      }
+    };
+    const uint64_t bias2 = pk2f(key_bias, key_bias);
+    for (int j = 0; j < n_local; ++j) {
+      const int s = j & 1, n = j >> 1;
+      const int64_t tile = tile0 + j;
+      const int cloud = (int)(tile / tiles_per_cloud);
+      if (cloud != cur_cloud) {
+        flush(cur_cloud);
+        cur_cloud = cloud;
+      }
+      mbar_wait(BAR(EU + s), n & 1);  // rstd2 of the tile's points
+      const float* rb = rbuf + (j & 3) * 128;
+      const uint32_t idx_base = (uint32_t)((int)(tile % tiles_per_cloud) * 128);
+      uint32_t v[32];
+#pragma unroll
+      for (int blk = 0; blk < NBLK; ++blk) {
+        const int g = j * NBLK + blk, r = g & 1, k = g >> 1;
+        mbar_wait(BAR(F2 + r), k & 1);
+        tc_fence_after();
+        const uint32_t t0 = tmem_base + 256u + (uint32_t)(r * 128) + lane_off;
+        uint32_t mk = 0;
+        float mm = m[blk];
+#pragma unroll
+        for (int ch = 0; ch < 128; ch += 32) {
+          tmem_ld32(t0 + ch, v);
+          if (ch == 96) {  // the whole block is in registers / consumed: hand the ring slot back before the last chunk's math
+            tc_fence_before();
+            mbar_arrive(BAR(D2 + r));
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 rr = *reinterpret_cast<const float4*>(rb + ch + i);  // broadcast
+            if (ARGMAX) {
+              // (bits(z + bias) & ~127) | (127 - point): z + bias > 0, so integer order is value order and the low 7
+              // mantissa bits carry the point, ties resolving to the smallest index
+              uint32_t z0, z1, z2, z3;
+              unpk2(fma2(pk2(v[i], v[i + 1]), pk2f(rr.x, rr.y), bias2), z0, z1);
+              unpk2(fma2(pk2(v[i + 2], v[i + 3]), pk2f(rr.z, rr.w), bias2), z2, z3);
+              z0 = (z0 & 0xffffff80u) | (uint32_t)(127 - (ch + i));
+              z1 = (z1 & 0xffffff80u) | (uint32_t)(127 - (ch + i + 1));
+              z2 = (z2 & 0xffffff80u) | (uint32_t)(127 - (ch + i + 2));
+              z3 = (z3 & 0xffffff80u) | (uint32_t)(127 - (ch + i + 3));
+              mk = __vimax3_u32(mk, z0, z1);
+              mk = __vimax3_u32(mk, z2, z3);
+            } else {
+              const uint64_t zero2 = pk2f(0.f, 0.f);
+              uint32_t z0, z1, z2, z3;
+              unpk2(fma2(pk2(v[i], v[i + 1]), pk2f(rr.x, rr.y), zero2), z0, z1);
+              unpk2(fma2(pk2(v[i + 2], v[i + 3]), pk2f(rr.z, rr.w), zero2), z2, z3);
+              mm = fmax3(mm, __uint_as_float(z0), __uint_as_float(z1));
+              mm = fmax3(mm, __uint_as_float(z2), __uint_as_float(z3));
+            }
+          }
+        }
+        if (ARGMAX) {
+          const uint32_t idx = idx_base + (127u - (mk & 127u));
+          const unsigned long long key = ((unsigned long long)(mk & 0xffffff80u) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+          run[blk] = max(run[blk], key);
+        } else {
+          m[blk] = mm;
+        }
+      }
+    }
+    if (n_local > 0) flush(cur_cloud);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+  }
+}
+
+// pooled[r][c] = relu(|g2[c]| * max_p z + b2[c]) and the argmax, from the packed (key, ~index) maxima
+__global__ void pool_finalize2_kernel(unsigned long long* __restrict__ keys, int R, int c3, const float* __restrict__ g2,
+                                      const float* __restrict__ be2, float key_bias, float* __restrict__ pooled,
+                                      int32_t* __restrict__ argmax) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)R * c3) return;
+  const int c = (int)(i % c3);
+  const unsigned long long k = keys[i];
+  keys[i] = 0ull;  // leave the scratch zeroed for the next call
+  const float z = __uint_as_float((uint32_t)(k >> 32)) - key_bias;
+  pooled[i] = fmaxf(fmaf(fabsf(g2[c]), z, be2[c]), 0.f);
+  if (argmax) argmax[i] = (int32_t)(0xFFFFFFFFu - (uint32_t)k);
+}
+
+__device__ __forceinline__ uint32_t img_off(int n, int k, int K) {
+  return (uint32_t)((n >> 3) * (K * 16) + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2);
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+// One launch packs everything; every block first derives the column means of W1 and W2 (the centring) in shared memory.
+__global__ void __launch_bounds__(256)
+pack_weights2_kernel(const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w1,
+                     const float* __restrict__ g1, const float* __restrict__ be1, const float* __restrict__ w2,
+                     const float* __restrict__ g2, const float* __restrict__ be2, int C, int c1, int c2, int c3,
+                     int rgb_u8, char* __restrict__ out) {
+  __shared__ float m1[128], m2[128];
+  {
+    const int t = threadIdx.x;
+    if (t < c1) {
+      float s = 0.f;
+      for (int n = 0; n < c2; ++n) s += w1[n * c1 + t];
+      m1[t] = s / (float)c2;
+    } else if (t >= 128 && t - 128 < c2) {
+      const int k = t - 128;
+      float s = 0.f;
+      for (int n = 0; n < c3; ++n) s += w2[n * c2 + k];
+      m2[k] = s / (float)c3;
+    }
+  }
+  __syncthreads();
+  const Wpack2 W = make_wpack2(c1, c2, c3);
+  const int n0 = c1 * 16, n1 = c2 * c1, n2 = c3 * c2, n3 = c2 * c2, n4 = 2 * c2 + 2 * c3;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n0) {
+    const int n = i / 16, k = i % 16;
+    float v = 0.f;
+    if (k < C) {
+      v = w0[n * C + k];
+      if (rgb_u8 && k >= 3 && k < 6) v *= (1.0f / 255.0f);  // staged rgb is the raw 0..255 integer
+    } else if (k == C) {
+      v = b0[n];  // multiplies the constant-1 channel
+    } else if (k <= C + 3) {
+      v = w0[n * C + (k - C - 1)];  // lo parts of xyz see the same weights
+    }
+    *reinterpret_cast<__nv_bfloat16*>(out + W.w0 + img_off(n, k, 16)) = __float2bfloat16(v);
+  } else if (i < n0 + n1) {
+    const int e = i - n0, n = e / c1, k = e % c1;
+    *reinterpret_cast<__nv_bfloat16*>(out + W.w1 + img_off(n, k, c1)) = __float2bfloat16(w1[e] - m1[k]);
+  } else if (i < n0 + n1 + n2) {
+    const int e = i - n0 - n1, n = e / c2, k = e % c2;
+    const float v = w2[e] - m2[k];
+    *reinterpret_cast<__nv_bfloat16*>(out + W.w2 + img_off(n, k, c2)) = __float2bfloat16(g2[n] >= 0.f ? v : -v);
+  } else if (i < n0 + n1 + n2 + n3) {
+    // Gram matrix of the centred, bf16-ROUNDED layer-2 weights (what the tensor core multiplies by): fp32 accumulate
+    const int e = i - n0 - n1 - n2, k = e / c2, kk = e % c2;
+    const float mk = m2[k], mkk = m2[kk];
+    float s = 0.f;
+    for (int n = 0; n < c3; ++n) s = fmaf(bf16_round(w2[n * c2 + k] - mk), bf16_round(w2[n * c2 + kk] - mkk), s);
+    *reinterpret_cast<__nv_bfloat16*>(out + W.gc + img_off(k, kk, c2)) = __float2bfloat16(s);
+  } else if (i < n0 + n1 + n2 + n3 + n4) {
+    const int e = i - n0 - n1 - n2 - n3;
+    if (e < c2) reinterpret_cast<float*>(out + W.prm1)[e] = g1[e];
+    else if (e < 2 * c2) reinterpret_cast<float*>(out + W.prm1)[e] = be1[e - c2];
+    else if (e < 2 * c2 + c3) reinterpret_cast<float*>(out + W.prm2)[e - 2 * c2] = g2[e - 2 * c2];
+    else reinterpret_cast<float*>(out + W.prm2)[e - 2 * c2] = be2[e - 2 * c2 - c3];
+  }
+}
+
+bool shapes_ok(int c1, int c2, int c3) {
+  return (c1 == 64 || c1 == 128) && c2 == 128 && (c3 == 128 || c3 == 256) && make_smem2(c1, c2, c3).total <= 227 * 1024;
+}
+
+int64_t wpack_bytes(int c1, int c2, int c3) { return shapes_ok(c1, c2, c3) ? (int64_t)make_wpack2(c1, c2, c3).total : 0; }
+
+int pack(const float* w0, const float* b0, const float* w1, const float* g1, const float* be1, const float* w2,
+         const float* g2, const float* be2, int C, int c1, int c2, int c3, int rgb_u8, void* wpack2, cudaStream_t st) {
+  const int n = c1 * 16 + c2 * c1 + c3 * c2 + c2 * c2 + 2 * c2 + 2 * c3;
+  pack_weights2_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(w0, b0, w1, g1, be1, w2, g2, be2, C, c1, c2, c3, rgb_u8,
+                                                                (char*)wpack2);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
+
+template <int C1, int C2, int NBLK>
+static int launch(const void* xh, const void* wpack2, int n_tiles, int tiles_per_cloud, int src_cloud_stride, float ln_eps,
+                  float key_bias, unsigned long long* keys, bool want_argmax, cudaStream_t st) {
+  const Smem2 L = make_smem2(C1, C2, NBLK * 128);
+  const int grid = std::min(sm_count(), n_tiles);
+  if (want_argmax) {
+    auto* kern = pointnet_fwd_tc2_kernel<C1, C2, NBLK, true>;
+    PCRL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    kern<<<grid, kThreads, L.total, st>>>((const char*)xh, (const char*)wpack2, n_tiles, tiles_per_cloud, src_cloud_stride,
+                                          ln_eps, key_bias, keys);
+  } else {
+    auto* kern = pointnet_fwd_tc2_kernel<C1, C2, NBLK, false>;
+    PCRL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    kern<<<grid, kThreads, L.total, st>>>((const char*)xh, (const char*)wpack2, n_tiles, tiles_per_cloud, src_cloud_stride,
+                                          ln_eps, key_bias, keys);
+  }
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
+
+// The fused forward + finalize.  wpack2: the second-generation image (pack()).
+int forward(const void* xh, int R, int src_cloud_stride, int NP, const void* wpack2, int c1, int c2, int c3, float ln_eps,
+            uint64_t* pool_keys, float* pooled, int32_t* argmax, cudaStream_t st) {
+  const int tiles_per_cloud = NP / 128;
+  const int n_tiles = R * tiles_per_cloud;
+  const float key_bias = 2.0f * sqrtf((float)c3);  // |xhat| < sqrt(c3): z + bias stays positive with margin
+  auto* keys = reinterpret_cast<unsigned long long*>(pool_keys);
+  int rc = PCRL_EUNSUPPORTED;
+  const bool am = argmax != nullptr;
+  if (c1 == 128 && c3 == 256) rc = launch<128, 128, 2>(xh, wpack2, n_tiles, tiles_per_cloud, src_cloud_stride, ln_eps, key_bias, keys, am, st);
+  else if (c1 == 64 && c3 == 256) rc = launch<64, 128, 2>(xh, wpack2, n_tiles, tiles_per_cloud, src_cloud_stride, ln_eps, key_bias, keys, am, st);
+  else if (c1 == 128 && c3 == 128) rc = launch<128, 128, 1>(xh, wpack2, n_tiles, tiles_per_cloud, src_cloud_stride, ln_eps, key_bias, keys, am, st);
+  else if (c1 == 64 && c3 == 128) rc = launch<64, 128, 1>(xh, wpack2, n_tiles, tiles_per_cloud, src_cloud_stride, ln_eps, key_bias, keys, am, st);
+  if (rc != PCRL_OK) return rc;
+  const int64_t n = (int64_t)R * c3;
+  const Wpack2 W = make_wpack2(c1, c2, c3);
+  const float* prm2 = reinterpret_cast<const float*>((const char*)wpack2 + W.prm2);
+  pool_finalize2_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(keys, R, c3, prm2, prm2 + c3, key_bias, pooled, argmax);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
+
+}  // namespace tc2
+}  // namespace pcrl

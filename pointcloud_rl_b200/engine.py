@@ -305,16 +305,32 @@ class UpdateEngine:
             self._pinned_np = [{k: v.numpy() for k, v in self._batch_views(p).items()} for p in self._pinned]
             self._pinned_ev = [None, None]
             self._pinned_i = 0
+            from concurrent.futures import ThreadPoolExecutor
+
+            self._copy_pool = ThreadPoolExecutor(max_workers=4, thread_name_prefix="pcrl-stage")
         i = self._pinned_i = self._pinned_i ^ 1
         if self._pinned_ev[i] is not None:
             self._pinned_ev[i].synchronize()
         host, views = self._pinned[i], self._pinned_np[i]
+        # host memcpy of the big leaves in row chunks on a few threads (numpy releases the GIL while it copies); the
+        # H2D copy of a chunk is enqueued as soon as its bytes are staged, so PCIe runs under the remaining memcpys
+        jobs = []
+        for key, _shape, _dt, off, nbytes in self._batch_layout:
+            src = self._host_leaf(batch, key)
+            dst = views[key]
+            src = src.reshape(dst.shape)
+            rows = dst.shape[0]
+            n_chunks = min(rows, max(1, nbytes // (1 << 20)))
+            step = -(-rows // n_chunks)
+            row_bytes = nbytes // rows
+            for r0 in range(0, rows, step):
+                r1 = min(rows, r0 + step)
+                fut = self._copy_pool.submit(np.copyto, dst[r0:r1], src[r0:r1], "unsafe")  # bool -> u8, f64 -> f32
+                jobs.append((fut, off + r0 * row_bytes, off + r1 * row_bytes))
         with torch.cuda.device(self.device):
-            for key, _shape, _dt, off, nbytes in self._batch_layout:
-                src = self._host_leaf(batch, key)
-                dst = views[key]
-                np.copyto(dst, src.reshape(dst.shape), casting="unsafe")  # bool -> u8, f64 -> f32 where needed
-                self.raw_flat[off:off + nbytes].copy_(host[off:off + nbytes], non_blocking=True)
+            for fut, b0, b1 in jobs:
+                fut.result()
+                self.raw_flat[b0:b1].copy_(host[b0:b1], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
             self._pinned_ev[i] = ev
