@@ -751,6 +751,8 @@ int pcrl_debug_set_fwd_version(int v) {
   g_fwd_version = v;
   return PCRL_OK;
 }
+int pcrl_debug_set_fwd2_flags(int flags) { return tc2::set_debug_flags(flags); }
+int pcrl_debug_get_trace2(long long* out_host) { return tc2::get_trace(out_host); }
 // first-generation image (also read by the backward's recompute), then the second-generation image, 128-byte aligned
 static int64_t wpack1_bytes(int c1, int c2, int c3) { return align_up((int64_t)tc::make_wpack(c1, c2, c3).total, 128); }
 

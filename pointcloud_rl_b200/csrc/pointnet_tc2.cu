@@ -46,6 +46,25 @@ constexpr int kStages = 3;
 constexpr int kTileBytes = 128 * 16 * 2;  // one X tile: 128 points x 16 bf16
 constexpr int kThreads = 512;
 
+// profiling knobs (tools/probe_fwd2.py): knock out individual passes to attribute time.  0 in production.
+//   1 pool math   2 Gram dot math   4 layer-1 normalise math   8 front-group TMEM loads   16 pool TMEM loads
+__device__ int g_dbg2 = 0;
+// clock64 trace of CTA 0 (flag 256): six roles x 512 (event, clock) pairs.  Compiled in only with -DPCRL_FWD_TRACE.
+__device__ long long g_trace2[6 * 1024];
+struct Tracer2 {
+  int region, n;
+  bool on;
+  __device__ __forceinline__ void operator()(int ev) {
+#ifdef PCRL_FWD_TRACE
+    if (on && n < 512) {
+      g_trace2[region * 1024 + 2 * n] = ev;
+      g_trace2[region * 1024 + 2 * n + 1] = clock64();
+      ++n;
+    }
+#endif
+  }
+};
+
 // Packed weight buffer, second generation (appended to the first generation's buffer, which the backward's dump mode
 // still reads):  [ W0' | W1c | Gc | W2c' | g1 be1 ]  <- one contiguous shared-memory image;  [ g2 be2 ] for the finalize
 struct Wpack2 {
@@ -87,6 +106,42 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return d;
 }
 
+struct NoOp {
+  __device__ __forceinline__ void operator()() const {}
+};
+// Walks NCH consecutive 32-column chunks of this warp's TMEM lanes with the loads software-pipelined over two register
+// buffers: chunk c+1 is in flight while f(chunk c, first column) runs.  last_loaded() runs as soon as the final
+// chunk's data is in registers (before its f).
+template <int NCH, class F, class G = NoOp>
+__device__ __forceinline__ void tmem_chunks(uint32_t taddr, bool skip_loads, F&& f, G&& last_loaded = NoOp()) {
+  uint32_t va[32], vb[32];
+  if (skip_loads) {  // profiling knock-out: no TMEM traffic, registers carry junk
+#pragma unroll
+    for (int i = 0; i < 32; ++i) va[i] = vb[i] = 0x3f800000u;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      if (c == NCH - 1) last_loaded();
+      f(va, c * 32);
+    }
+    return;
+  }
+  tmem_ld32_async(taddr, va);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    if (c & 1) {
+      tmem_wait_ld_dep(vb);
+      if (c + 1 < NCH) tmem_ld32_async(taddr + 32 * (c + 1), va);
+      if (c == NCH - 1) last_loaded();
+      f(vb, c * 32);
+    } else {
+      tmem_wait_ld_dep(va);
+      if (c + 1 < NCH) tmem_ld32_async(taddr + 32 * (c + 1), vb);
+      if (c == NCH - 1) last_loaded();
+      f(va, c * 32);
+    }
+  }
+}
+
 template <int C1, int C2, int NBLK, bool ARGMAX>
 __global__ void __launch_bounds__(kThreads, 1)
 pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wpack, int n_tiles, int tiles_per_cloud,
@@ -96,7 +151,7 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
   const Smem2 L = make_smem2(C1, C2, C3);
   const Wpack2 W = make_wpack2(C1, C2, C3);
   const uint32_t sbase = smem_u32(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // provably warp-uniform
   constexpr uint32_t kActBytes = 128 * (C1 > C2 ? C1 : C2) * 2;
 
   // mbarriers
@@ -112,7 +167,8 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
   constexpr int HF = EU + 2;        // [slot] the transposed layer-2 MMAs have finished reading the slot's h1
   constexpr int F2 = HF + 2;        // [ring] transposed layer-2 accumulator complete
   constexpr int D2 = F2 + 2;        // [ring] ... drained by the pool group (128 arrivals)
-  constexpr int NBAR = D2 + 2;
+  constexpr int UI = D2 + 2;        // [slot] the Gram MMA has been ISSUED (the transposed layer 2 queues behind it)
+  constexpr int NBAR = UI + 2;
   const uint32_t bar0 = sbase + L.bars;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L.bars + NBAR * 8);
@@ -133,6 +189,7 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
       mbar_init(BAR(HF + s), 1);
       mbar_init(BAR(F2 + s), 1);
       mbar_init(BAR(D2 + s), 128);
+      mbar_init(BAR(UI + s), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -145,6 +202,13 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+#if defined(PCRL_FWD_KNOCKOUT)
+  const int dbg = g_dbg2;  // knock-outs put branches into the inner loops (no load hoisting across them): profiling builds only
+#elif defined(PCRL_FWD_TRACE)
+  const int dbg = g_dbg2 & 256;  // tracer only
+#else
+  constexpr int dbg = 0;
+#endif
 
   // every CTA takes a contiguous range of tiles (consecutive tiles belong to the same cloud)
   const int t_q = n_tiles / (int)gridDim.x, t_r = n_tiles % (int)gridDim.x;
@@ -173,56 +237,79 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
     }
   } else if (warp == 1 || warp == 2) {
     // ------------------------------------------------------------------ MMA issuer of one tile slot: layer 0, layer 1, Gram
-    if (lane == 0) {
-      const int s = warp - 1;
-      const uint32_t tm = tmem_base + (uint32_t)(s * 128);
-      const uint32_t act = sbase + L.act + (uint32_t)s * kActBytes;
-      const uint32_t id0 = make_idesc(C1), id1 = make_idesc(C2);
-      mbar_wait(BAR(WB), 0);
-      for (int j = s; j < n_local; j += 2) {
-        const int n = j >> 1, st = j % kStages;
-        mbar_wait(BAR(XF + st), (j / kStages) & 1);
-        if (n > 0) mbar_wait(BAR(EU + s), (n - 1) & 1);  // the slot's previous tile has drained U
-        tc_fence_after();
-        mma_bf16(tm, make_desc(sbase + L.xst + st * kTileBytes, 256), make_desc(s_w0, 256), id0, 0);
+    // (warp-uniform control flow, one elected lane issues: see elect_one())
+    const int s = __shfl_sync(0xffffffffu, warp - 1, 0);
+    const uint32_t tm = tmem_base + (uint32_t)(s * 128);
+    const uint32_t act = sbase + L.act + (uint32_t)s * kActBytes;
+    const uint32_t id0 = make_idesc(C1), id1 = make_idesc(C2);
+    const uint64_t d_w0 = make_desc(s_w0, 256), d_w1 = make_desc(s_w1, C1 * 16), d_gc = make_desc(s_gc, C2 * 16);
+    const uint64_t d_h0 = make_desc(act, C1 * 16), d_h1 = make_desc(act, C2 * 16);
+    uint64_t d_x[kStages];
+#pragma unroll
+    for (int st = 0; st < kStages; ++st) d_x[st] = make_desc(sbase + L.xst + st * kTileBytes, 256);
+    mbar_wait(BAR(WB), 0);
+    Tracer2 tr{s, 0, (dbg & 256) && blockIdx.x == 0 && lane == 0};
+    for (int j = s; j < n_local; j += 2) {
+      const int n = j >> 1, st = j % kStages;
+      mbar_wait(BAR(XF + st), (j / kStages) & 1);
+      if (n > 0) mbar_wait(BAR(EU + s), (n - 1) & 1);  // the slot's previous tile has drained U
+      tr(1000 * j + 100);
+      tc_fence_after();
+      if (elect_one()) {
+        mma_bf16(tm, st == 0 ? d_x[0] : (st == 1 ? d_x[1] : d_x[2]), d_w0, id0, 0);
         mma_commit(BAR(XE + st));
         mma_commit(BAR(F0 + s));
-        mbar_wait(BAR(E0 + s), n & 1);  // h0 in shared memory, acc0 drained
-        tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < C1 / 16; ++ks)
-          mma_bf16(tm, make_desc(act + ks * 256, C1 * 16), make_desc(s_w1 + ks * 256, C1 * 16), id1, ks > 0);
-        mma_commit(BAR(F1 + s));
-        mbar_wait(BAR(E1 + s), n & 1);  // h1 in shared memory, acc1 drained
-        tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < C2 / 16; ++ks)
-          mma_bf16(tm, make_desc(act + ks * 256, C2 * 16), make_desc(s_gc + ks * 256, C2 * 16), id1, ks > 0);
-        mma_commit(BAR(FU + s));
       }
+      __syncwarp();
+      mbar_wait(BAR(E0 + s), n & 1);  // h0 in shared memory, acc0 drained
+      tr(1000 * j + 110);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < C1 / 16; ++ks) mma_bf16(tm, desc_kstep(d_h0, ks), desc_kstep(d_w1, ks), id1, ks > 0);
+        mma_commit(BAR(F1 + s));
+      }
+      __syncwarp();
+      mbar_wait(BAR(E1 + s), n & 1);  // h1 in shared memory, acc1 drained
+      tr(1000 * j + 120);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < C2 / 16; ++ks) mma_bf16(tm, desc_kstep(d_h1, ks), desc_kstep(d_gc, ks), id1, ks > 0);
+        mma_commit(BAR(FU + s));
+        mbar_arrive(BAR(UI + s));
+      }
+      __syncwarp();
+      tr(1000 * j + 220);
     }
   } else if (warp == 3) {
     // ------------------------------------------------------------------ MMA issuer of the transposed layer 2
-    if (lane == 0) {
-      const uint32_t idT = make_idesc(128);  // N = the tile's 128 points
-      mbar_wait(BAR(WB), 0);
-      for (int j = 0; j < n_local; ++j) {
-        const int s = j & 1, n = j >> 1;
-        const uint32_t act = sbase + L.act + (uint32_t)s * kActBytes;
-        mbar_wait(BAR(E1 + s), n & 1);  // h1 of tile j in shared memory
+    const uint32_t idT = make_idesc(128);  // N = the tile's 128 points
+    const uint64_t d_w2 = make_desc(s_w2, C2 * 16);
+    const uint64_t d_a0 = make_desc(sbase + L.act, C2 * 16), d_a1 = make_desc(sbase + L.act + kActBytes, C2 * 16);
+    mbar_wait(BAR(WB), 0);
+    Tracer2 tr{2, 0, (dbg & 256) && blockIdx.x == 0 && lane == 0};
+    for (int j = 0; j < n_local; ++j) {
+      const int s = j & 1, n = j >> 1;
+      const uint64_t d_h1 = s ? d_a1 : d_a0;
+      // h1 of tile j is in shared memory AND its Gram MMA is already in the tensor pipe's queue: the front group's
+      // chain (U -> rstd2 -> next tile of the slot) is the latency-critical one, the pool group only needs throughput
+      mbar_wait(BAR(UI + s), n & 1);
 #pragma unroll
-        for (int blk = 0; blk < NBLK; ++blk) {
-          const int g = j * NBLK + blk, r = g & 1, k = g >> 1;
-          if (k > 0) mbar_wait(BAR(D2 + r), (k - 1) & 1);  // the pool group drained the ring slot's previous block
-          tc_fence_after();
+      for (int blk = 0; blk < NBLK; ++blk) {
+        const int g = j * NBLK + blk, r = g & 1, k = g >> 1;
+        if (k > 0) mbar_wait(BAR(D2 + r), (k - 1) & 1);  // the pool group drained the ring slot's previous block
+        tr(1000 * j + 130 + blk);
+        tc_fence_after();
+        if (elect_one()) {
           const uint32_t d = tmem_base + 256u + (uint32_t)(r * 128);
-          const uint32_t wa = s_w2 + (uint32_t)blk * 16u * (uint32_t)(C2 * 16);  // rows 128 blk .. of the W2c' image
+          const uint64_t wa = d_w2 + (uint64_t)(blk * 16 * C2);  // rows 128 blk .. of the W2c' image: 16 groups x C2*16 bytes, >> 4
 #pragma unroll
-          for (int ks = 0; ks < C2 / 16; ++ks)
-            mma_bf16(d, make_desc(wa + ks * 256, C2 * 16), make_desc(act + ks * 256, C2 * 16), idT, ks > 0);
+          for (int ks = 0; ks < C2 / 16; ++ks) mma_bf16(d, desc_kstep(wa, ks), desc_kstep(d_h1, ks), idT, ks > 0);
           mma_commit(BAR(F2 + r));
+          if (blk == NBLK - 1) mma_commit(BAR(HF + s));  // every MMA that reads the slot's h1 buffer has completed when this fires
         }
-        mma_commit(BAR(HF + s));  // every MMA that reads the slot's h1 buffer has completed when this fires
+        __syncwarp();
       }
     }
   } else if (warp < 12) {
@@ -237,17 +324,18 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
     unsigned char* dst0 = abuf + (row >> 3) * (uint32_t)(C1 * 16) + (row & 7) * 16;
     unsigned char* dst1 = abuf + (row >> 3) * (uint32_t)(C2 * 16) + (row & 7) * 16;
     float* rbuf = reinterpret_cast<float*>(smem + L.rbuf);
+    const bool no_ld = dbg & 8;
     mbar_wait(BAR(WB), 0);  // LN parameters landed
+    Tracer2 tr{3 + s, 0, (dbg & 256) && blockIdx.x == 0 && lane == 0 && q == 0};
     for (int j = s; j < n_local; j += 2) {
       const int n = j >> 1;
-      uint32_t v[32];
       // ---- layer 0: ReLU -> bf16 operand of layer 1
       mbar_wait(BAR(F0 + s), n & 1);
+      tr(1000 * j + 300);
       if (n > 0) mbar_wait(BAR(HF + s), (n - 1) & 1);  // the previous tile's transposed layer 2 no longer reads the buffer
+      tr(1000 * j + 301);
       tc_fence_after();
-#pragma unroll
-      for (int ch = 0; ch < C1; ch += 32) {
-        tmem_ld32(taddr + ch, v);
+      tmem_chunks<C1 / 32>(taddr, no_ld, [&](uint32_t(&v)[32], int ch) {
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           uint4 o;
@@ -257,25 +345,26 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
           o.w = pack_relu_bf16x2(__uint_as_float(v[8 * jj + 6]), __uint_as_float(v[8 * jj + 7]));
           *reinterpret_cast<uint4*>(dst0 + ((ch >> 3) + jj) * 128) = o;
         }
-      }
+      });
       fence_async_smem();
       tc_fence_before();
       mbar_arrive(BAR(E0 + s));
+      tr(1000 * j + 310);
 
       // ---- layer 1: the accumulator holds y - mean(y) (centred weights): variance, normalise, affine, ReLU
       mbar_wait(BAR(F1 + s), n & 1);
+      tr(1000 * j + 320);
       tc_fence_after();
       uint64_t q01 = pk2f(0.f, 0.f), q23 = q01;
-#pragma unroll
-      for (int ch = 0; ch < C2; ch += 32) {
-        tmem_ld32(taddr + ch, v);
+      tmem_chunks<C2 / 32>(taddr, no_ld, [&](uint32_t(&v)[32], int) {
+        if (dbg & 4) return;
 #pragma unroll
         for (int jj = 0; jj < 32; jj += 4) {
           const uint64_t y01 = pk2(v[jj], v[jj + 1]), y23 = pk2(v[jj + 2], v[jj + 3]);
           q01 = fma2(y01, y01, q01);
           q23 = fma2(y23, y23, q23);
         }
-      }
+      });
       float rstd1;
       {
         uint32_t a, b, c, d;
@@ -284,45 +373,51 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
         const float sq = (__uint_as_float(a) + __uint_as_float(b)) + (__uint_as_float(c) + __uint_as_float(d));
         rstd1 = rsqrtf(sq * (1.0f / (float)C2) + ln_eps);
       }
-      uint32_t hp[C2 / 2];  // this row's h1 as packed bf16 pairs: the Gram dot below needs it again
       const uint64_t r2 = pk2f(rstd1, rstd1);
-#pragma unroll
-      for (int ch = 0; ch < C2; ch += 32) {
-        tmem_ld32(taddr + ch, v);
+      tmem_chunks<C2 / 32>(taddr, no_ld, [&](uint32_t(&v)[32], int ch) {
+        uint32_t hp[16];
 #pragma unroll
         for (int j4 = 0; j4 < 32; j4 += 4) {
+          if (dbg & 4) {
+            hp[j4 / 2] = v[j4];
+            hp[j4 / 2 + 1] = v[j4 + 2];
+            continue;
+          }
           const float4 gg = *reinterpret_cast<const float4*>(g1 + ch + j4);
           const float4 bb = *reinterpret_cast<const float4*>(be1 + ch + j4);
           const uint64_t zero2 = pk2f(0.f, 0.f);
           uint32_t x0, x1, x2, x3;
           unpk2(fma2(fma2(pk2(v[j4], v[j4 + 1]), r2, zero2), pk2f(gg.x, gg.y), pk2f(bb.x, bb.y)), x0, x1);
           unpk2(fma2(fma2(pk2(v[j4 + 2], v[j4 + 3]), r2, zero2), pk2f(gg.z, gg.w), pk2f(bb.z, bb.w)), x2, x3);
-          hp[(ch + j4) / 2] = pack_relu_bf16x2(__uint_as_float(x0), __uint_as_float(x1));
-          hp[(ch + j4) / 2 + 1] = pack_relu_bf16x2(__uint_as_float(x2), __uint_as_float(x3));
+          hp[j4 / 2] = pack_relu_bf16x2(__uint_as_float(x0), __uint_as_float(x1));
+          hp[j4 / 2 + 1] = pack_relu_bf16x2(__uint_as_float(x2), __uint_as_float(x3));
         }
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj)
-          *reinterpret_cast<uint4*>(dst1 + ((ch >> 3) + jj) * 128) =
-              make_uint4(hp[ch / 2 + 4 * jj], hp[ch / 2 + 4 * jj + 1], hp[ch / 2 + 4 * jj + 2], hp[ch / 2 + 4 * jj + 3]);
-      }
+          *reinterpret_cast<uint4*>(dst1 + ((ch >> 3) + jj) * 128) = make_uint4(hp[4 * jj], hp[4 * jj + 1], hp[4 * jj + 2], hp[4 * jj + 3]);
+      });
       fence_async_smem();
       tc_fence_before();
       mbar_arrive(BAR(E1 + s));
+      tr(1000 * j + 330);
 
-      // ---- variance of layer 2: sum_c (y2_c - mean)^2 = h1 . (Gc h1) = dot(h1, U)
+      // ---- variance of layer 2: sum_c (y2_c - mean)^2 = h1 . (Gc h1) = dot(h1, U); h1 (this thread's own row) is read
+      // back from the operand buffer it has just written
       mbar_wait(BAR(FU + s), n & 1);
+      tr(1000 * j + 340);
       tc_fence_after();
       uint64_t d01 = pk2f(0.f, 0.f), d23 = d01;
+      tmem_chunks<C2 / 32>(taddr, no_ld, [&](uint32_t(&v)[32], int ch) {
+        if (dbg & 2) return;
 #pragma unroll
-      for (int ch = 0; ch < C2; ch += 32) {
-        tmem_ld32(taddr + ch, v);
-#pragma unroll
-        for (int jj = 0; jj < 32; jj += 4) {
-          const uint32_t p0 = hp[(ch + jj) / 2], p1 = hp[(ch + jj) / 2 + 1];
-          d01 = fma2(pk2(v[jj], v[jj + 1]), pk2(p0 << 16, p0 & 0xffff0000u), d01);
-          d23 = fma2(pk2(v[jj + 2], v[jj + 3]), pk2(p1 << 16, p1 & 0xffff0000u), d23);
+        for (int jj = 0; jj < 4; ++jj) {
+          const uint4 h = *reinterpret_cast<const uint4*>(dst1 + ((ch >> 3) + jj) * 128);  // channels ch + 8 jj .. + 7
+          d01 = fma2(pk2(v[8 * jj + 0], v[8 * jj + 1]), pk2(h.x << 16, h.x & 0xffff0000u), d01);
+          d23 = fma2(pk2(v[8 * jj + 2], v[8 * jj + 3]), pk2(h.y << 16, h.y & 0xffff0000u), d23);
+          d01 = fma2(pk2(v[8 * jj + 4], v[8 * jj + 5]), pk2(h.z << 16, h.z & 0xffff0000u), d01);
+          d23 = fma2(pk2(v[8 * jj + 6], v[8 * jj + 7]), pk2(h.w << 16, h.w & 0xffff0000u), d23);
         }
-      }
+      });
       {
         uint32_t a, b, c, d;
         unpk2(d01, a, b);
@@ -332,6 +427,7 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
       }
       tc_fence_before();
       mbar_arrive(BAR(EU + s));
+      tr(1000 * j + 350);
     }
   } else {
     // ------------------------------------------------------------------ pool group: scale by rstd2[point], running max over points
@@ -362,6 +458,7 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
       }
     };
     const uint64_t bias2 = pk2f(key_bias, key_bias);
+    Tracer2 tr{5, 0, (dbg & 256) && blockIdx.x == 0 && lane == 0 && q == 0};
     for (int j = 0; j < n_local; ++j) {
       const int s = j & 1, n = j >> 1;
       const int64_t tile = tile0 + j;
@@ -371,24 +468,20 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
         cur_cloud = cloud;
       }
       mbar_wait(BAR(EU + s), n & 1);  // rstd2 of the tile's points
+      tr(1000 * j + 400);
       const float* rb = rbuf + (j & 3) * 128;
       const uint32_t idx_base = (uint32_t)((int)(tile % tiles_per_cloud) * 128);
-      uint32_t v[32];
 #pragma unroll
       for (int blk = 0; blk < NBLK; ++blk) {
         const int g = j * NBLK + blk, r = g & 1, k = g >> 1;
         mbar_wait(BAR(F2 + r), k & 1);
+        tr(1000 * j + 410 + blk);
         tc_fence_after();
         const uint32_t t0 = tmem_base + 256u + (uint32_t)(r * 128) + lane_off;
-        uint32_t mk = 0;
-        float mm = m[blk];
-#pragma unroll
-        for (int ch = 0; ch < 128; ch += 32) {
-          tmem_ld32(t0 + ch, v);
-          if (ch == 96) {  // the whole block is in registers / consumed: hand the ring slot back before the last chunk's math
-            tc_fence_before();
-            mbar_arrive(BAR(D2 + r));
-          }
+        uint32_t mk0 = 0, mk1 = 0;        // two independent max chains
+        float mm0 = m[blk], mm1 = -3.0e38f;
+        tmem_chunks<4>(t0, (dbg & 16) != 0, [&](uint32_t(&v)[32], int ch) {
+          if (dbg & 1) return;
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const float4 rr = *reinterpret_cast<const float4*>(rb + ch + i);  // broadcast
@@ -402,25 +495,30 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
               z1 = (z1 & 0xffffff80u) | (uint32_t)(127 - (ch + i + 1));
               z2 = (z2 & 0xffffff80u) | (uint32_t)(127 - (ch + i + 2));
               z3 = (z3 & 0xffffff80u) | (uint32_t)(127 - (ch + i + 3));
-              mk = __vimax3_u32(mk, z0, z1);
-              mk = __vimax3_u32(mk, z2, z3);
+              mk0 = __vimax3_u32(mk0, z0, z1);
+              mk1 = __vimax3_u32(mk1, z2, z3);
             } else {
               const uint64_t zero2 = pk2f(0.f, 0.f);
               uint32_t z0, z1, z2, z3;
               unpk2(fma2(pk2(v[i], v[i + 1]), pk2f(rr.x, rr.y), zero2), z0, z1);
               unpk2(fma2(pk2(v[i + 2], v[i + 3]), pk2f(rr.z, rr.w), zero2), z2, z3);
-              mm = fmax3(mm, __uint_as_float(z0), __uint_as_float(z1));
-              mm = fmax3(mm, __uint_as_float(z2), __uint_as_float(z3));
+              mm0 = fmax3(mm0, __uint_as_float(z0), __uint_as_float(z1));
+              mm1 = fmax3(mm1, __uint_as_float(z2), __uint_as_float(z3));
             }
           }
-        }
+        }, [&]() {  // every column of the block has been read: hand the ring slot back before the last chunk's math
+          tc_fence_before();
+          mbar_arrive(BAR(D2 + r));
+        });
         if (ARGMAX) {
+          const uint32_t mk = max(mk0, mk1);
           const uint32_t idx = idx_base + (127u - (mk & 127u));
           const unsigned long long key = ((unsigned long long)(mk & 0xffffff80u) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
           run[blk] = max(run[blk], key);
         } else {
-          m[blk] = mm;
+          m[blk] = fmaxf(mm0, mm1);
         }
+        tr(1000 * j + 420 + blk);
       }
     }
     if (n_local > 0) flush(cur_cloud);
@@ -567,6 +665,17 @@ int forward(const void* xh, int R, int src_cloud_stride, int NP, const void* wpa
   pool_finalize2_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(keys, R, c3, prm2, prm2 + c3, key_bias, pooled, argmax);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
+}
+
+int set_debug_flags(int flags) {
+  PCRL_CHECK_CUDA(cudaMemcpyToSymbol(g_dbg2, &flags, sizeof(int)));
+  static long long zeros[6 * 1024] = {0};
+  PCRL_CHECK_CUDA(cudaMemcpyToSymbol(g_trace2, zeros, sizeof(zeros)));
+  return PCRL_OK;
+}
+int get_trace(long long* out_host) {
+  PCRL_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_trace2, sizeof(long long) * 6 * 1024));
+  return 6 * 512;
 }
 
 }  // namespace tc2

@@ -11,5 +11,7 @@ int pack(const float* w0, const float* b0, const float* w1, const float* g1, con
          const float* g2, const float* be2, int C, int c1, int c2, int c3, int rgb_u8, void* wpack2, cudaStream_t st);
 int forward(const void* xh, int R, int src_cloud_stride, int NP, const void* wpack2, int c1, int c2, int c3, float ln_eps,
             uint64_t* pool_keys, float* pooled, int32_t* argmax, cudaStream_t st);
+int set_debug_flags(int flags);
+int get_trace(long long* out_host);
 }  // namespace tc2
 }  // namespace pcrl

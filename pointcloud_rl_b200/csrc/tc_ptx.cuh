@@ -89,6 +89,17 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// One lane of a converged warp.  The MMA-issuing warps run their loops warp-uniformly and elect a lane only around the
+// tcgen05 instructions: under `if (lane == 0)` the compiler cannot prove that descriptor / address operands are
+// warp-uniform and wraps every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~70 cycles per MMA, more than
+// the 64 cycles an M = 128, N = 128, K = 16 MMA computes for).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// descriptor of K-step `ks` (16 bf16 = two 128-byte core matrices = 256 bytes) from the descriptor of K-step 0
+__device__ __forceinline__ uint64_t desc_kstep(uint64_t d0, int ks) { return d0 + (uint64_t)(ks * 16); }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -115,6 +126,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// tcgen05.wait::ld that the compiler cannot move register reads across: the 32 destination registers of an earlier
+// tmem_ld32_async are in/out operands, so every use of them is ordered after the wait (software-pipelined TMEM loads)
+__device__ __forceinline__ void tmem_wait_ld_dep(uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+        "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+        "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+        "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+      :
+      : "memory");
 }
 // two fp32 -> packed bf16x2 with ReLU; `lo` lands in the low half (lower channel / lower address)
 __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {

@@ -93,5 +93,46 @@ for ver in (1, 2):
         res[(ver, want)] = eng.w["pooled_next"].clone()
         print(f"v{ver} argmax={int(want)}: {ms*1e3:7.1f} us  {ms*1e-3*1.965e9/(tiles/148):7.0f} cyc/tile  {fl/ms/1e9:7.1f} TFLOP/s  "
               f"= {fl/ms/1e9/1673*100:.1f} % of 1673")
+L.cdll.pcrl_debug_set_fwd_version(ctypes.c_int(2))
+for flags, name in [(1, "no pool math"), (2, "no Gram dot math"), (4, "no layer-1 normalise math"), (1 + 2 + 4, "no epilogue math at all"),
+                    (1 + 16, "no pool math, no pool TMEM loads"), (2 + 4 + 8, "no front math, no front TMEM loads"),
+                    (31, "sync skeleton + MMAs only")]:
+    L.cdll.pcrl_debug_set_fwd2_flags(ctypes.c_int(flags))
+    ts = []
+    for i in range(8):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.pointnet_fwd_bf16(eng.w["xh_next"], R, spec.n_points, spec.NP, eng.w["wpack"], c1, c2, c3, spec.ln_eps,
+                            eng.w["pool_keys_next"], eng.w["pooled_next"], None, st)
+        e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = float(np.mean(ts[3:]))
+    print(f"knock-out {flags:2d} {name:40s} {ms*1e3:7.1f} us  {ms*1e-3*1.965e9/(tiles/148):7.0f} cyc/tile")
+# ---- clock64 trace of CTA 0 (needs a build with PCRL_NVCC_EXTRA=-DPCRL_FWD_TRACE)
+if os.environ.get("PCRL_TRACE"):
+    for flags in [int(x) for x in os.environ["PCRL_TRACE"].split(",")]:
+        L.cdll.pcrl_debug_set_fwd2_flags(ctypes.c_int(flags | 256))
+        L.pointnet_fwd_bf16(eng.w["xh_next"], R, spec.n_points, spec.NP, eng.w["wpack"], c1, c2, c3, spec.ln_eps,
+                            eng.w["pool_keys_next"], eng.w["pooled_next"], None, st)
+        torch.cuda.synchronize()
+        buf = (ctypes.c_longlong * (6 * 1024))()
+        L.cdll.pcrl_debug_get_trace2(buf)
+        ev = []
+        for reg in range(6):
+            for i in range(512):
+                e, t = buf[reg * 1024 + 2 * i], buf[reg * 1024 + 2 * i + 1]
+                if t:
+                    ev.append((t, reg, e))
+        ev.sort()
+        t0 = ev[0][0] if ev else 0
+        names = ["iss0", "iss1", "issT", "frn0", "frn1", "pool"]
+        print(f"--- trace, knock-out flags {flags}: role, tile, event (1xx issuer woke: 100 L0 / 110 L1 / 120 U, 220 U issued; 13b issT woke for block b;"
+              " 300 F0, 301 HF, 310 E0 sent, 320 F1, 330 E1 sent, 340 FU, 350 EU sent; 400 pool got rstd, 41b block ready, 42b block done)")
+        for t, reg, e in ev:
+            tile = e // 1000
+            if 12 <= tile <= 15:
+                print(f"{t - t0:8d}  {names[reg]}  tile {tile:2d}  {e % 1000}")
+L.cdll.pcrl_debug_set_fwd2_flags(ctypes.c_int(0))
 print("config-2 pooled v2 vs v1 rel diff:", rel(res[(2, False)], res[(1, False)]))
 L.cdll.pcrl_debug_set_fwd_version(ctypes.c_int(0))
