@@ -142,6 +142,19 @@ __device__ __forceinline__ void tmem_chunks(uint32_t taddr, bool skip_loads, F&&
   }
 }
 
+// single register buffer (for the passes that keep a row of packed activations live beside the chunk)
+template <int NCH, class F>
+__device__ __forceinline__ void tmem_chunks1(uint32_t taddr, bool skip_loads, F&& f) {
+  uint32_t v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = 0x3f800000u;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    if (!skip_loads) tmem_ld32(taddr + 32 * c, v);
+    f(v, c * 32);
+  }
+}
+
 template <int C1, int C2, int NBLK, bool ARGMAX>
 __global__ void __launch_bounds__(kThreads, 1)
 pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wpack, int n_tiles, int tiles_per_cloud,
@@ -374,13 +387,14 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
         rstd1 = rsqrtf(sq * (1.0f / (float)C2) + ln_eps);
       }
       const uint64_t r2 = pk2f(rstd1, rstd1);
-      tmem_chunks<C2 / 32>(taddr, no_ld, [&](uint32_t(&v)[32], int ch) {
-        uint32_t hp[16];
+      uint32_t hp[C2 / 2];  // this row's h1 as packed bf16 pairs: the Gram dot below needs it again (registers, not a
+                            // shared-memory read-back: the shared-memory pipe is what this kernel runs out of)
+      tmem_chunks1<C2 / 32>(taddr, no_ld, [&](uint32_t(&v)[32], int ch) {
 #pragma unroll
         for (int j4 = 0; j4 < 32; j4 += 4) {
           if (dbg & 4) {
-            hp[j4 / 2] = v[j4];
-            hp[j4 / 2 + 1] = v[j4 + 2];
+            hp[(ch + j4) / 2] = v[j4];
+            hp[(ch + j4) / 2 + 1] = v[j4 + 2];
             continue;
           }
           const float4 gg = *reinterpret_cast<const float4*>(g1 + ch + j4);
@@ -389,33 +403,31 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
           uint32_t x0, x1, x2, x3;
           unpk2(fma2(fma2(pk2(v[j4], v[j4 + 1]), r2, zero2), pk2f(gg.x, gg.y), pk2f(bb.x, bb.y)), x0, x1);
           unpk2(fma2(fma2(pk2(v[j4 + 2], v[j4 + 3]), r2, zero2), pk2f(gg.z, gg.w), pk2f(bb.z, bb.w)), x2, x3);
-          hp[j4 / 2] = pack_relu_bf16x2(__uint_as_float(x0), __uint_as_float(x1));
-          hp[j4 / 2 + 1] = pack_relu_bf16x2(__uint_as_float(x2), __uint_as_float(x3));
+          hp[(ch + j4) / 2] = pack_relu_bf16x2(__uint_as_float(x0), __uint_as_float(x1));
+          hp[(ch + j4) / 2 + 1] = pack_relu_bf16x2(__uint_as_float(x2), __uint_as_float(x3));
         }
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj)
-          *reinterpret_cast<uint4*>(dst1 + ((ch >> 3) + jj) * 128) = make_uint4(hp[4 * jj], hp[4 * jj + 1], hp[4 * jj + 2], hp[4 * jj + 3]);
+          *reinterpret_cast<uint4*>(dst1 + ((ch >> 3) + jj) * 128) =
+              make_uint4(hp[ch / 2 + 4 * jj], hp[ch / 2 + 4 * jj + 1], hp[ch / 2 + 4 * jj + 2], hp[ch / 2 + 4 * jj + 3]);
       });
       fence_async_smem();
       tc_fence_before();
       mbar_arrive(BAR(E1 + s));
       tr(1000 * j + 330);
 
-      // ---- variance of layer 2: sum_c (y2_c - mean)^2 = h1 . (Gc h1) = dot(h1, U); h1 (this thread's own row) is read
-      // back from the operand buffer it has just written
+      // ---- variance of layer 2: sum_c (y2_c - mean)^2 = h1 . (Gc h1) = dot(h1, U)
       mbar_wait(BAR(FU + s), n & 1);
       tr(1000 * j + 340);
       tc_fence_after();
       uint64_t d01 = pk2f(0.f, 0.f), d23 = d01;
-      tmem_chunks<C2 / 32>(taddr, no_ld, [&](uint32_t(&v)[32], int ch) {
+      tmem_chunks1<C2 / 32>(taddr, no_ld, [&](uint32_t(&v)[32], int ch) {
         if (dbg & 2) return;
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const uint4 h = *reinterpret_cast<const uint4*>(dst1 + ((ch >> 3) + jj) * 128);  // channels ch + 8 jj .. + 7
-          d01 = fma2(pk2(v[8 * jj + 0], v[8 * jj + 1]), pk2(h.x << 16, h.x & 0xffff0000u), d01);
-          d23 = fma2(pk2(v[8 * jj + 2], v[8 * jj + 3]), pk2(h.y << 16, h.y & 0xffff0000u), d23);
-          d01 = fma2(pk2(v[8 * jj + 4], v[8 * jj + 5]), pk2(h.z << 16, h.z & 0xffff0000u), d01);
-          d23 = fma2(pk2(v[8 * jj + 6], v[8 * jj + 7]), pk2(h.w << 16, h.w & 0xffff0000u), d23);
+        for (int jj = 0; jj < 32; jj += 4) {
+          const uint32_t p0 = hp[(ch + jj) / 2], p1 = hp[(ch + jj) / 2 + 1];
+          d01 = fma2(pk2(v[jj], v[jj + 1]), pk2(p0 << 16, p0 & 0xffff0000u), d01);
+          d23 = fma2(pk2(v[jj + 2], v[jj + 3]), pk2(p1 << 16, p1 & 0xffff0000u), d23);
         }
       });
       {
