@@ -297,6 +297,21 @@ class RotatingMemory:
         return self._wrap(b)
 
 
+def build_engine(w, precision, device, seed):
+    """Bare UpdateEngine of a workload (tools/*.py: kernel probes and timelines below the agent API)."""
+    from pointcloud_rl_b200.engine import HyperParams, PathSpec, UpdateEngine
+    from pointcloud_rl_b200.synthetic import init_params
+
+    spec = PathSpec(n_points=w["N"], action_dim=w["A"], state_dim=w["S"], n_pos=w["n_pos"], n_seg=w["n_seg"],
+                    widths=w["widths"], out_dim=w["D"], hidden=w["hidden"])
+    k = w["num_aug"] if w["algo"] == "drq" else 1
+    hp = HyperParams(algo=w["algo"], gamma=w["gamma"], num_aug=k, aug=w["aug"], aug_lo=w["aug_lo"], aug_hi=w["aug_hi"])
+    eng = UpdateEngine(spec, hp, batch_size=w["B"], device=device, precision=precision, seed=seed)
+    eng.load_params(init_params(0, spec, zero_out_logstd=w["zero_out_logstd"]))
+    eng.prime_alpha()
+    return eng, spec
+
+
 def build_bench_agent(w, precision, device, seed, use_graph=True):
     from pointcloud_rl_b200.synthetic import make_agent
 

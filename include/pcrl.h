@@ -110,6 +110,14 @@ int pcrl_pointnet_pack_weights(const float* w0, const float* b0, const float* w1
                                const float* w2, const float* g2, const float* be2, int C, int c1, int c2, int c3,
                                int rgb_u8 /* xh holds raw 0..255 rgb: fold 1/255 into w0 */, void* wpack,
                                void* stream);
+/* Same, restricted to one of the two images inside `wpack`: PCRL_WPACK_FWD = what pcrl_pointnet_fwd_bf16 reads (on the
+ * critical path of every encode), PCRL_WPACK_BWD = what pcrl_pointnet_bwd's recompute reads (needed only ~0.4 ms later,
+ * so the caller can pack it on a side stream, and not at all before an encode that has no backward). */
+#define PCRL_WPACK_FWD 1
+#define PCRL_WPACK_BWD 2
+int pcrl_pointnet_pack_weights_part(const float* w0, const float* b0, const float* w1, const float* g1, const float* be1,
+                                    const float* w2, const float* g2, const float* be2, int C, int c1, int c2, int c3,
+                                    int rgb_u8, int which /* PCRL_WPACK_FWD | PCRL_WPACK_BWD */, void* wpack, void* stream);
 int pcrl_pointnet_fwd_bf16(const void* xh, int R, int N, int NP, const void* wpack, int c1, int c2, int c3,
                            float ln_eps, uint64_t* pool_keys /* [R,c3] scratch: zero before the first call, every call leaves it zeroed */, float* pooled, int32_t* argmax,
                            void* stream);

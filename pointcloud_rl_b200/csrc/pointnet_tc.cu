@@ -758,23 +758,35 @@ static int64_t wpack1_bytes(int c1, int c2, int c3) { return align_up((int64_t)t
 
 int64_t pcrl_pointnet_wpack_bytes(int c1, int c2, int c3) { return wpack1_bytes(c1, c2, c3) + tc2::wpack_bytes(c1, c2, c3); }
 
-int pcrl_pointnet_pack_weights(const float* w0, const float* b0, const float* w1, const float* g1, const float* be1,
-                               const float* w2, const float* g2, const float* be2, int C, int c1, int c2, int c3,
-                               int rgb_u8, void* wpack, void* stream) {
+int pcrl_pointnet_pack_weights_part(const float* w0, const float* b0, const float* w1, const float* g1, const float* be1,
+                                    const float* w2, const float* g2, const float* be2, int C, int c1, int c2, int c3,
+                                    int rgb_u8, int which, void* wpack, void* stream) {
   PCRL_CHECK_ARG(w0 && b0 && w1 && g1 && be1 && w2 && g2 && be2 && wpack);
   if (C + 4 > 16 || !tc::shapes_ok(c1, c2, c3)) {
     set_error("pcrl_pointnet_pack_weights: shape unsupported by the tcgen05 path (C=%d <= 12, widths (%d,%d,%d) multiples of 64/64/128 "
               "up to 256 with max(c1,c2) + 1.5*c3 <= 512 TMEM columns); use the fp32 path", C, c1, c2, c3);
     return PCRL_EUNSUPPORTED;
   }
-  const int n = c1 * 16 + c2 * c1 + c3 * c2 + 2 * c2 + 2 * c3 + c3;
-  tc::pack_weights_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(w0, b0, w1, g1, be1, w2, g2, be2, C,
-                                                                                   c1, c2, c3, rgb_u8, (char*)wpack);
-  PCRL_CHECK_LAUNCH();
-  if (tc2::shapes_ok(c1, c2, c3))
+  const bool v2 = tc2::shapes_ok(c1, c2, c3);
+  // the first-generation image feeds the backward's recompute, and the forward too where the second generation
+  // does not cover the shape
+  if ((which & PCRL_WPACK_BWD) || ((which & PCRL_WPACK_FWD) && !v2)) {
+    const int n = c1 * 16 + c2 * c1 + c3 * c2 + 2 * c2 + 2 * c3 + c3;
+    tc::pack_weights_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(w0, b0, w1, g1, be1, w2, g2, be2, C,
+                                                                                     c1, c2, c3, rgb_u8, (char*)wpack);
+    PCRL_CHECK_LAUNCH();
+  }
+  if ((which & PCRL_WPACK_FWD) && v2)
     return tc2::pack(w0, b0, w1, g1, be1, w2, g2, be2, C, c1, c2, c3, rgb_u8, (char*)wpack + wpack1_bytes(c1, c2, c3),
                      as_stream(stream));
   return PCRL_OK;
+}
+
+int pcrl_pointnet_pack_weights(const float* w0, const float* b0, const float* w1, const float* g1, const float* be1,
+                               const float* w2, const float* g2, const float* be2, int C, int c1, int c2, int c3,
+                               int rgb_u8, void* wpack, void* stream) {
+  return pcrl_pointnet_pack_weights_part(w0, b0, w1, g1, be1, w2, g2, be2, C, c1, c2, c3, rgb_u8,
+                                         PCRL_WPACK_FWD | PCRL_WPACK_BWD, wpack, stream);
 }
 
 int pcrl_pointnet_fwd_bf16(const void* xh, int R, int N, int NP, const void* wpack, int c1, int c2, int c3,

@@ -68,7 +68,7 @@ struct Tracer2 {
 // Packed weight buffer, second generation (appended to the first generation's buffer, which the backward's dump mode
 // still reads):  [ W0' | W1c | Gc | W2c' | g1 be1 ]  <- one contiguous shared-memory image;  [ g2 be2 ] for the finalize
 struct Wpack2 {
-  uint32_t w0, w1, gc, w2, prm1, img_bytes, prm2, total;
+  uint32_t w0, w1, gc, w2, prm1, img_bytes, prm2, cm, total;
 };
 __host__ __device__ inline Wpack2 make_wpack2(int c1, int c2, int c3) {
   Wpack2 W;
@@ -80,6 +80,7 @@ __host__ __device__ inline Wpack2 make_wpack2(int c1, int c2, int c3) {
   W.prm1 = o; o += 2 * c2 * 4;
   W.img_bytes = o;
   W.prm2 = o; o += 2 * c3 * 4;
+  W.cm = o;   o += (c1 + c2) * 4;  // column means of W1 and W2 (scratch of the packer)
   W.total = (o + 127) & ~127u;
   return W;
 }
@@ -563,28 +564,35 @@ __device__ __forceinline__ uint32_t img_off(int n, int k, int K) {
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
-// One launch packs everything; every block first derives the column means of W1 and W2 (the centring) in shared memory.
+// Column means of W1 (over its c2 rows) and W2 (over its c3 rows): block 0 / block 1, 1024 threads = 8 row groups x
+// (up to) 128 columns, reduced through shared memory.  ~1.5 us; the packer reads the result.
+__global__ void __launch_bounds__(1024)
+colmean_kernel(const float* __restrict__ w1, const float* __restrict__ w2, int c1, int c2, int c3, float* __restrict__ cm) {
+  __shared__ float part[8][128];
+  const float* w = blockIdx.x == 0 ? w1 : w2;
+  const int rows = blockIdx.x == 0 ? c2 : c3, cols = blockIdx.x == 0 ? c1 : c2;
+  const int k = threadIdx.x & 127, g = threadIdx.x >> 7;
+  float s = 0.f;
+  if (k < cols)
+    for (int n = g; n < rows; n += 8) s += w[n * cols + k];
+  part[g][k] = s;
+  __syncthreads();
+  if (g == 0 && k < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][k];
+    cm[(blockIdx.x == 0 ? 0 : c1) + k] = t / (float)rows;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 pack_weights2_kernel(const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w1,
                      const float* __restrict__ g1, const float* __restrict__ be1, const float* __restrict__ w2,
                      const float* __restrict__ g2, const float* __restrict__ be2, int C, int c1, int c2, int c3,
                      int rgb_u8, char* __restrict__ out) {
-  __shared__ float m1[128], m2[128];
-  {
-    const int t = threadIdx.x;
-    if (t < c1) {
-      float s = 0.f;
-      for (int n = 0; n < c2; ++n) s += w1[n * c1 + t];
-      m1[t] = s / (float)c2;
-    } else if (t >= 128 && t - 128 < c2) {
-      const int k = t - 128;
-      float s = 0.f;
-      for (int n = 0; n < c3; ++n) s += w2[n * c2 + k];
-      m2[k] = s / (float)c3;
-    }
-  }
-  __syncthreads();
   const Wpack2 W = make_wpack2(c1, c2, c3);
+  const float* m1 = reinterpret_cast<const float*>(out + W.cm);
+  const float* m2 = m1 + c1;
   const int n0 = c1 * 16, n1 = c2 * c1, n2 = c3 * c2, n3 = c2 * c2, n4 = 2 * c2 + 2 * c3;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n0) {
@@ -607,12 +615,18 @@ pack_weights2_kernel(const float* __restrict__ w0, const float* __restrict__ b0,
     const float v = w2[e] - m2[k];
     *reinterpret_cast<__nv_bfloat16*>(out + W.w2 + img_off(n, k, c2)) = __float2bfloat16(g2[n] >= 0.f ? v : -v);
   } else if (i < n0 + n1 + n2 + n3) {
-    // Gram matrix of the centred, bf16-ROUNDED layer-2 weights (what the tensor core multiplies by): fp32 accumulate
+    // Gram matrix of the centred, bf16-ROUNDED layer-2 weights (what the tensor core multiplies by): fp32 accumulate,
+    // four independent chains over the c3 rows
     const int e = i - n0 - n1 - n2, k = e / c2, kk = e % c2;
     const float mk = m2[k], mkk = m2[kk];
-    float s = 0.f;
-    for (int n = 0; n < c3; ++n) s = fmaf(bf16_round(w2[n * c2 + k] - mk), bf16_round(w2[n * c2 + kk] - mkk), s);
-    *reinterpret_cast<__nv_bfloat16*>(out + W.gc + img_off(k, kk, c2)) = __float2bfloat16(s);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    for (int n = 0; n < c3; n += 4) {
+      s0 = fmaf(bf16_round(w2[n * c2 + k] - mk), bf16_round(w2[n * c2 + kk] - mkk), s0);
+      s1 = fmaf(bf16_round(w2[(n + 1) * c2 + k] - mk), bf16_round(w2[(n + 1) * c2 + kk] - mkk), s1);
+      s2 = fmaf(bf16_round(w2[(n + 2) * c2 + k] - mk), bf16_round(w2[(n + 2) * c2 + kk] - mkk), s2);
+      s3 = fmaf(bf16_round(w2[(n + 3) * c2 + k] - mk), bf16_round(w2[(n + 3) * c2 + kk] - mkk), s3);
+    }
+    *reinterpret_cast<__nv_bfloat16*>(out + W.gc + img_off(k, kk, c2)) = __float2bfloat16((s0 + s1) + (s2 + s3));
   } else if (i < n0 + n1 + n2 + n3 + n4) {
     const int e = i - n0 - n1 - n2 - n3;
     if (e < c2) reinterpret_cast<float*>(out + W.prm1)[e] = g1[e];
@@ -631,6 +645,8 @@ int64_t wpack_bytes(int c1, int c2, int c3) { return shapes_ok(c1, c2, c3) ? (in
 int pack(const float* w0, const float* b0, const float* w1, const float* g1, const float* be1, const float* w2,
          const float* g2, const float* be2, int C, int c1, int c2, int c3, int rgb_u8, void* wpack2, cudaStream_t st) {
   const int n = c1 * 16 + c2 * c1 + c3 * c2 + c2 * c2 + 2 * c2 + 2 * c3;
+  colmean_kernel<<<2, 1024, 0, st>>>(w1, w2, c1, c2, c3, reinterpret_cast<float*>((char*)wpack2 + make_wpack2(c1, c2, c3).cm));
+  PCRL_CHECK_LAUNCH();
   pack_weights2_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(w0, b0, w1, g1, be1, w2, g2, be2, C, c1, c2, c3, rgb_u8,
                                                                 (char*)wpack2);
   PCRL_CHECK_LAUNCH();

@@ -269,7 +269,8 @@ class UpdateEngine:
         # side streams 0-2 carry branches of the critical chain (target branch, second Q head): high priority, like the
         # capture stream; 3-8 carry the weight-gradient GEMMs that only feed the optimizer: default (low) priority, so
         # the block scheduler hands free SMs to the dX chain first
-        self._side = ([torch.cuda.Stream(device=dev, priority=-1 if i < 3 else 0) for i in range(9)]
+        # 9 carries the packing of the backward's weight image (joined right before the PointNet backward)
+        self._side = ([torch.cuda.Stream(device=dev, priority=-1 if i < 3 else 0) for i in range(10)]
                       if dev.type == "cuda" else [])
         self._capture_stream = torch.cuda.Stream(device=dev, priority=-1) if dev.type == "cuda" else None
         self._landing = None
@@ -422,15 +423,16 @@ class UpdateEngine:
     def dominant_kernel_name(self):
         return "pointnet_fwd_tc_kernel" if self.precision == "bf16" else "pointnet_fwd_f32 chain"
 
-    def _pack_weights(self, st):
-        """bf16 path: re-pack the (just updated) PointNet weights into the MMA-ready smem image."""
+    def _pack_weights(self, st, which=3):
+        """bf16 path: re-pack the (just updated) PointNet weights into the MMA-ready images.  which: 1 = the image the
+        fused forward reads (critical path of every encode), 2 = the image the backward's recompute reads, 3 = both."""
         if self.precision != "bf16":
             return
         sp, p = self.spec, self.p
         c1, c2, c3 = sp.widths
-        self.L.pointnet_pack_weights(p["pn.w0"], p["pn.b0"], p["pn.w1"], p["pn.g1"], p["pn.be1"], p["pn.w2"],
-                                     p["pn.g2"], p["pn.be2"], sp.C, c1, c2, c3, int(sp.has_rgb and sp.rgb_u8),
-                                     self.w["wpack"], st)
+        self.L.pointnet_pack_weights_part(p["pn.w0"], p["pn.b0"], p["pn.w1"], p["pn.g1"], p["pn.be1"], p["pn.w2"],
+                                          p["pn.g2"], p["pn.be2"], sp.C, c1, c2, c3, int(sp.has_rgb and sp.rgb_u8), which,
+                                          self.w["wpack"], st)
 
     def _mlp_fwd(self, net, x, K, M, out, ldo, nout, keep, st):
         p, (h1n, h2n) = self.p, self.spec.hidden
@@ -569,8 +571,11 @@ class UpdateEngine:
 
         # weight packing only feeds the encodes: it runs beside the two staging kernels
         s_p = self._fork(3)
+        s_pb = self._fork(9)
+        with torch.cuda.stream(s_pb):
+            self._pack_weights(ST(), 2)  # read by the backward's recompute ~0.4 ms from now: off the critical path
         with torch.cuda.stream(s_p):
-            self._pack_weights(ST())
+            self._pack_weights(ST(), 1)
             if self.actor_w0p is not None:  # refreshed every update: the parameters may have been written from outside
                 L.copy_cols(p["actor.w0"], D + S, 1, 1, self.actor_w0p, self.actor_w0p.shape[1], 0, sp.hidden[0], D + S,
                             ST())
@@ -642,6 +647,7 @@ class UpdateEngine:
         L.linear_bwd(w["pooled_obs"], c3, p["pn.wf"], w["dz"], D, self.g["pn.wf"], self.g["pn.bf"], w["dpooled"], c3,
                      None, 0, R, c3, D, self.tf32, ST())
         g = self.g
+        self._join(s_pb)
         L.pointnet_bwd(w["xf_obs"], R, sp.n_points, sp.NP, sp.CP, sp.C, w["pooled_obs"], w["argmax_obs"], w["dpooled"],
                        p["pn.w0"], p["pn.b0"], p["pn.w1"], p["pn.g1"], p["pn.be1"], p["pn.w2"], p["pn.g2"],
                        p["pn.be2"], c1, c2, c3, sp.ln_eps, g["pn.w0"], g["pn.b0"], g["pn.w1"], g["pn.g1"], g["pn.be1"],
@@ -661,7 +667,7 @@ class UpdateEngine:
                 name = "pi"
             else:
                 name = "obs"
-            self._pack_weights(ST())
+            self._pack_weights(ST(), 1)  # no backward follows this encode
             self._encode(name, B, False, ST())  # post-critic-step PointNet weights; output detached
             cat = w[f"cat_{name}"]
             if S:

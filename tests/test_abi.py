@@ -26,7 +26,12 @@ def test_library_exports_every_declared_symbol():
     assert isinstance(L.last_error(), str)
     # pure-host queries work without a GPU
     img = 128 * 32 + 128 * 128 * 2 + 256 * 128 * 2 + (256 + 512) * 4  # W0' | W1 | signed/permuted W2 | LN parameters
-    assert L.pointnet_wpack_bytes(128, 128, 256) == img + 256 * 4 + 16 + 256 * 128 * 2  # + permutation, n_pos, plain W2
+    gen1 = img + 256 * 4 + 16 + 256 * 128 * 2  # + permutation, n_pos, plain W2 (the backward's recompute image)
+    gen1 = (gen1 + 127) // 128 * 128
+    # second-generation forward image: W0' | centred W1 | Gram(W2c) | centred signed W2 | g1 be1 | g2 be2 | column means
+    gen2 = 128 * 32 + 128 * 128 * 2 + 128 * 128 * 2 + 256 * 128 * 2 + 2 * 128 * 4 + 2 * 256 * 4 + (128 + 128) * 4
+    gen2 = (gen2 + 127) // 128 * 128
+    assert L.pointnet_wpack_bytes(128, 128, 256) == gen1 + gen2
     assert L.pointnet_fwd_f32_workspace(2, 1280, 128, 128, 256) == 2 * 1280 * 512 * 4
     assert L.pointnet_bwd_workspace(4, 256, 128, 128, 256, 8) > 0
 
