@@ -85,6 +85,17 @@ int pcrl_downsample_map(int N, float drop_ratio, int fixed_ratio, uint64_t seed,
 int pcrl_gather_transitions(const uint64_t* src_ptrs, const uint64_t* dst_ptrs, const int64_t* row_bytes, int n_leaves,
                             const int64_t* idx, int B, void* stream);
 
+/* ColorJitterPoints (pyrl/utils/augmentations/pcd_aug.py:269-303 -> torchvision ColorJitter on [B',3,1,N] uint8):
+ * rgb u8 [B,3,N] -> out u8 [B,3,N].  One parameter set per CALL is shared by all clouds (so the num_aug copies of a
+ * sample are identical: run it on the B source clouds and let pcrl_stage_points repeat them).
+ * params_dev: NULL = draw from Philox (seed, *counter_dev, stream_id); else 8 device floats
+ * [order0..3 (a permutation of 0 brightness, 1 contrast, 2 saturation, 3 hue), brightness, contrast, saturation, hue
+ * factors] = the reference's draws (parity mode).  brightness / contrast / saturation / hue: the config magnitudes
+ * (factor ranges [max(0,1-x), 1+x]; hue [-h, h], h <= 0.5).  Bit-exact vs torchvision 0.26 for uint8 input. */
+int pcrl_color_jitter_points(const uint8_t* rgb, int B, int N, const float* params_dev, float brightness, float contrast,
+                             float saturation, float hue, uint64_t seed, const uint64_t* counter_dev, uint32_t stream_id,
+                             uint8_t* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (2) PointNet per-point shared MLP + max-pool.  Replaces ConvMLP (mlp.py:15-94; block_utils.py),
  * LN1d (nn_layer.py:192-225) and feature.max(-1) (pointnet.py:151):

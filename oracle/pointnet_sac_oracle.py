@@ -201,6 +201,29 @@ def aug_downsample(obs, index):
     return {k: (v[..., index] if k in ("xyz", "rgb", "seg", "pos_encoding") else v) for k, v in obs.items()}
 
 
+def aug_colorjitter(rgb, params):
+    """ColorJitterPoints.process_single, pcd_aug.py:291-295: torchvision ColorJitter.forward on rgb[:, :, None, :]
+    (uint8 [B',3,1,N]).  torchvision is a third-party dependency of the reference (environment.yml); its forward is
+    restated here with the draws injected: params = [order0..3, brightness, contrast, saturation, hue] -- the op order
+    (a permutation of 0 brightness, 1 contrast, 2 saturation, 3 hue) and one factor per op, shared by the whole batch --
+    calling torchvision's own adjust_* functions."""
+    import torchvision.transforms.functional as TF
+
+    img = torch.as_tensor(rgb)[:, :, None, :]
+    order = [int(v) for v in params[:4]]
+    b, c, s, h = (float(v) for v in params[4:8])
+    for fn_id in order:
+        if fn_id == 0:
+            img = TF.adjust_brightness(img, b)
+        elif fn_id == 1:
+            img = TF.adjust_contrast(img, c)
+        elif fn_id == 2:
+            img = TF.adjust_saturation(img, s)
+        elif fn_id == 3:
+            img = TF.adjust_hue(img, h)
+    return img.squeeze(-2)
+
+
 def _apply_aug(obs, hp, noise, which):
     obs = dict(obs)
     kind = hp.get("aug", None)
@@ -212,6 +235,8 @@ def _apply_aug(obs, hp, noise, which):
         obs["xyz"] = aug_shift(obs["xyz"], noise[f"shift_{which}"])
     elif kind == "downsample":
         obs = aug_downsample(obs, noise[f"keep_{which}"].long())
+    elif kind == "colorjitter":
+        obs["rgb"] = aug_colorjitter(obs["rgb"], noise[f"cj_{which}"])
     elif kind is not None:
         raise ValueError(kind)
     return obs
@@ -311,7 +336,8 @@ def update(state, batch, updates, hp, noise, capture=None, idx_override=None):
 
     batch: dict(obs=dict, next_obs=dict, actions [B,A], rewards [B,1], dones [B,1]) of numpy / torch.
     noise: injected randomness -- jitter_obs / jitter_next [B*num_aug,3,N] (or angle_obs / angle_next
-           [B*num_aug,1], or shift_obs / shift_next [B*num_aug,3], or keep_obs / keep_next [N'] kept point indices), eps_next [B*num_aug,A], eps_pi [B,A].
+           [B*num_aug,1], or shift_obs / shift_next [B*num_aug,3], or keep_obs / keep_next [N'] kept point indices, or
+           cj_obs / cj_next [8] colour-jitter order + factors), eps_next [B*num_aug,A], eps_pi [B,A].
     Mutates `state` in place, returns the reference's scalar dict.  `capture` (a dict) receives
     intermediates for the parity tests.
     """

@@ -228,11 +228,12 @@ class SAC(BaseAgent):
 
     def _hyper(self):
         kind, lo, hi, *rest = (None, 0.0, 0.0) if self._aug is None else self._aug
-        axes = rest[0] if rest else 7
+        axes = rest[0] if (rest and kind == "shift") else 7
+        color = tuple(rest[0]) if (rest and kind == "colorjitter") else (0.0, 0.0, 0.0, 0.0)
         head = self.actor.head
         return HyperParams(
             algo=self.PREFIX, gamma=float(self.gamma), reward_scale=float(self.reward_scale), num_aug=self._num_aug,
-            aug=kind, aug_lo=lo, aug_hi=hi, aug_axes=axes, tau=self._tau, actor_update_interval=self.actor_update_interval,
+            aug=kind, aug_lo=lo, aug_hi=hi, aug_axes=axes, aug_color=color, tau=self._tau, actor_update_interval=self.actor_update_interval,
             target_update_interval=self.target_update_interval, lr=self.critic_optim.defaults["lr"],
             actor_lr=self.actor_optim.defaults["lr"], alpha_lr=self.alpha_optim.defaults["lr"],
             betas=self.critic_optim.defaults["betas"], actor_betas=self.actor_optim.defaults["betas"], alpha_betas=self.alpha_optim.defaults["betas"],

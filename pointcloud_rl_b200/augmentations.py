@@ -147,6 +147,56 @@ class RandomDownSample(BaseAugmentation):
         return f"RandomDownSample(drop_ratio={self.drop_ratio}, fixed_ratio={self.fixed_ratio})"
 
 
+@AUGMENTATIONS.register_module()
+class ColorJitterPoints(BaseAugmentation):
+    """torchvision ColorJitter on the uint8 point colours viewed as a [B', 3, 1, N] image batch (pcd_aug.py:269-303;
+    `pn_colorjitter.py`: brightness = contrast = saturation = 0.4, hue = 0.5).  One random op order and one factor
+    per op are drawn per CALL and shared by the whole batch (torchvision semantics).  Runs as pcrl_color_jitter_points."""
+
+    kind = "colorjitter"
+
+    def __init__(self, main_key="inputs/rgb", req_keys="inputs/rgb", brightness=0.5, contrast=0.5, saturation=0.5, hue=0.5):
+        req_keys = [req_keys] if isinstance(req_keys, str) else req_keys
+        super().__init__(main_key, req_keys)
+        if brightness < 0 or brightness > 1:
+            raise ValueError("brightness shoud be non-negative")
+        if contrast < 0 or contrast > 1:
+            raise ValueError("contrast shoud be non-negative")
+        if saturation < 0 or saturation > 1:
+            raise ValueError("saturation shoud be non-negative")
+        if hue < 0 or hue > 0.5:
+            raise ValueError("hue shoud be non-negative")
+        self.brightness, self.contrast, self.saturation, self.hue = float(brightness), float(contrast), float(saturation), float(hue)
+
+    def params(self):
+        return self.kind, 0.0, 0.0, (self.brightness, self.contrast, self.saturation, self.hue)
+
+    def __call__(self, data):
+        """Rollout-side use (DrQ.inference_aug): the same kernel on device uint8 colours."""
+        from ._lib import lib, stream_ptr
+
+        data = dict(data)
+        for key in self.req_keys:
+            if key in data:
+                x = data[key]
+                if x.dtype != torch.uint8 or not x.is_cuda:
+                    raise NotImplementedError("ColorJitterPoints runs on device uint8 colours [B,3,N]")
+                x = x.contiguous()
+                out = torch.empty_like(x)
+                if not hasattr(self, "_counter"):
+                    self._counter = torch.zeros(1, dtype=torch.int64, device=x.device)
+                with torch.cuda.device(x.device):
+                    lib().color_jitter_points(x, x.shape[0], x.shape[-1], None, self.brightness, self.contrast,
+                                              self.saturation, self.hue, 0x5EED, self._counter, 6, out, stream_ptr())
+                self._counter.add_(1)
+                data[key] = out
+        return data
+
+    def __repr__(self):
+        return (f"ColorJitterPoints(brightness={self.brightness},contrast={self.contrast},saturation={self.saturation},"
+                f"hue={self.hue})")
+
+
 class DataAugmentations:
     def __init__(self, transforms):
         self.transforms = [build_from_cfg(t, AUGMENTATIONS) if isinstance(t, dict) else t for t in transforms]

@@ -89,5 +89,9 @@ def shift(translation_range):
                 translation_range=list(translation_range), shift_height=True)
 
 
+COLOR_JITTER = dict(type="ColorJitterPoints", main_key="rgb", req_keys=["rgb"], brightness=0.4, contrast=0.4,
+                    saturation=0.4, hue=0.5)
+
+
 def dropout(req_keys):
     return dict(type="RandomDownSample", main_key="xyz", req_keys=list(req_keys), drop_ratio=0.3, fixed_ratio=False)

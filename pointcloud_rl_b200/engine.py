@@ -22,7 +22,7 @@ S_NAMES = [
     "entropy", "actor_grad_sq", "alpha", "alpha_grad",
 ]
 NUM_SCALARS = 16
-AUG_KINDS = {None: 0, "none": 0, "jitter": 1, "rot": 2, "shift": 3, "downsample": 4}
+AUG_KINDS = {None: 0, "none": 0, "jitter": 1, "rot": 2, "shift": 3, "downsample": 4, "colorjitter": 5}
 MLP_KEYS = ["w0", "b0", "w1", "b1", "w2", "b2"]
 PN_KEYS = ["pn.w0", "pn.b0", "pn.w1", "pn.g1", "pn.be1", "pn.w2", "pn.g2", "pn.be2", "pn.wf", "pn.bf", "pn.gf", "pn.bef"]
 
@@ -95,6 +95,7 @@ class HyperParams:
     aug_lo: float = 0.0
     aug_hi: float = 0.0
     aug_axes: int = 7  # shift only: bit i set = axis i is translated (include/pcrl.h, PCRL_AUG_SHIFT_AXES)
+    aug_color: Tuple[float, float, float, float] = (0.0, 0.0, 0.0, 0.0)  # colorjitter: brightness, contrast, saturation, hue
     tau: float = 0.01
     actor_update_interval: int = 2
     target_update_interval: int = 2
@@ -217,6 +218,11 @@ class UpdateEngine:
 
         w = {}
         bf16 = self.precision == "bf16"
+        if self.hp.algo == "drq" and self.hp.aug == "colorjitter":
+            if not (sp.has_rgb and sp.rgb_u8):
+                raise NotImplementedError("ColorJitterPoints needs uint8 point colours (torchvision's uint8 path)")
+            w["rgb_aug_next"] = torch.zeros(B, 3, N, **u8)
+            w["rgb_aug_obs"] = torch.zeros(B, 3, N, **u8)
         if self.hp.algo == "drq" and self.hp.aug == "downsample":
             w["ds_map_next"] = torch.zeros(N, dtype=torch.int32, device=dev)
             w["ds_map_obs"] = torch.zeros(N, dtype=torch.int32, device=dev)
@@ -383,8 +389,17 @@ class UpdateEngine:
     # ------------------------------------------------------------------ building blocks
     def _stage(self, which, name, repeat, aug_kind, noise, stream_id, st):
         sp, raw = self.spec, self.raw[which]
+        rgb = raw.get("rgb")
+        if aug_kind == 5:
+            # ColorJitterPoints: one parameter set per call is shared by the whole batch, so the num_aug copies of a
+            # sample are identical: jitter the B source clouds once, the staging kernel repeats them
+            c = self.hp.aug_color
+            rgb = self.w[f"rgb_aug_{name}"]
+            self.L.color_jitter_points(raw["rgb"], self.B, sp.n_points, noise, float(c[0]), float(c[1]), float(c[2]),
+                                       float(c[3]), self.seed, self.counter, stream_id, rgb, st)
+            aug_kind, noise = 0, None
         self.L.stage_points(
-            raw["xyz"], raw.get("rgb"), int(sp.rgb_u8), raw.get("pos_encoding"), sp.n_pos, raw.get("seg"), sp.n_seg,
+            raw["xyz"], rgb, int(sp.rgb_u8), raw.get("pos_encoding"), sp.n_pos, raw.get("seg"), sp.n_seg,
             self.B, sp.n_points, repeat, aug_kind, float(self.hp.aug_lo), float(self.hp.aug_hi), noise, self.seed,
             self.counter, stream_id, self.w.get(f"xf_{name}"), self.w.get(f"xh_{name}"), sp.CP, st)
 
@@ -547,7 +562,7 @@ class UpdateEngine:
         c1, c2, c3 = sp.widths
         noise = noise or {}
         aug = AUG_KINDS[hp.aug] if hp.algo == "drq" else 0
-        nkey = {1: "jitter", 2: "angle", 3: "shift", 4: "keep"}.get(aug)
+        nkey = {1: "jitter", 2: "angle", 3: "shift", 4: "keep", 5: "cj"}.get(aug)
         if aug == 3:
             aug |= (int(hp.aug_axes) & 7) << 8
         if aug == 4:

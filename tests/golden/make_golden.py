@@ -60,6 +60,11 @@ def draw_noise(seed, algo, aug, k, B, N, A, with_actor, rng):
             elif aug == "downsample":  # pcd_aug.py:244-251 + array_ops.py:659-673; rng = (drop_ratio, fixed_ratio)
                 n_drop = int(N * rng[0]) if rng[1] else np.random.randint(int(N * rng[0]))
                 noise[f"keep_{which}"] = torch.rand(1, N).argsort(1)[0, : N - n_drop].clone()
+            elif aug == "colorjitter":  # torchvision ColorJitter.get_params: randperm(4), then one uniform per op
+                order = torch.randperm(4)
+                f = [float(torch.empty(1).uniform_(max(0.0, 1 - m), 1 + m)) for m in rng[:3]]
+                f.append(float(torch.empty(1).uniform_(-rng[3], rng[3])))
+                noise[f"cj_{which}"] = torch.tensor([float(v) for v in order] + f, dtype=torch.float64)
             elif aug == "shift":  # pcd_aug.py:193, translation_range = [hi, hi, hi]
                 noise[f"shift_{which}"] = (torch.rand([B * k, 3]) - 0.5) * 2 * torch.tensor([rng[1]] * 3, dtype=torch.float)
     noise["eps_next"] = _standard_normal((B * k, A), dtype=torch.float32, device=torch.device("cpu"))
@@ -107,6 +112,7 @@ def gen_update_fixture(ns, name, cfg_path, algo, aug, aug_rng, B, N, A, n_seg, n
         flatten(f"after{u}/", O.params_from_reference_state_dict(agent.state_dict()), out)
     meta = dict(
         algo=algo, aug=aug or "", aug_lo=aug_rng[0] if aug_rng else 0.0, aug_hi=aug_rng[1] if aug_rng else 0.0,
+        **({f"cj_{n}": float(v) for n, v in zip("bcsh", aug_rng)} if aug == "colorjitter" else {}),
         B=B, N=N, A=A, n_seg=n_seg, n_pos=n_pos, S=S, num_aug=k, n_updates=n_updates,
         gamma=float(agent.gamma), reward_scale=float(agent.reward_scale),
         target_entropy=float(agent.target_entropy), tau=float(agent.update_coeff["default"]),
@@ -157,6 +163,10 @@ def main():
     if "--only-downsample" in sys.argv:  # added after the other fixtures were committed; they are not regenerated
         gen_update_fixture(ns, "drq_downsample_small", "configs/mfrl/drq/maniskill/pn_dropout.py", "drq", "downsample",
                            (0.3, 0), B=5, N=80, A=4, n_seg=2, n_pos=0, S=9, dup=False)
+        return
+    if "--only-colorjitter" in sys.argv:  # added in round 2; the other fixtures are not regenerated
+        gen_update_fixture(ns, "drq_colorjitter_small", "configs/mfrl/drq/maniskill/pn_colorjitter.py", "drq", "colorjitter",
+                           (0.4, 0.4, 0.4, 0.5), B=5, N=88, A=4, n_seg=1, n_pos=0, S=9, dup=False)
         return
     if "--only-shift" in sys.argv:  # added after the other fixtures were committed; they are not regenerated
         gen_update_fixture(ns, "drq_shift_small", "configs/mfrl/drq/maniskill/pn_shift.py", "drq", "shift", (-0.1, 0.1),

@@ -207,7 +207,8 @@ def test_device_replay_ring_matches_a_host_ring():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("rel", ["mfrl/drq/maniskill/pn_shift.py", "mfrl/drq/maniskill/pn_dropout.py"])
+@pytest.mark.parametrize("rel", ["mfrl/drq/maniskill/pn_shift.py", "mfrl/drq/maniskill/pn_dropout.py",
+                                 "mfrl/drq/maniskill/pn_colorjitter.py"])
 def test_widened_augmentation_configs_run_through_the_public_call(rel):
     """pn_shift.py / pn_dropout.py: agent from the config, graph-replayed updates with the
     device-side (Philox) draws, finite logged scalars with the reference's keys."""

@@ -10,7 +10,8 @@ from pointcloud_rl_b200.meta import ConfigDict, Registry, build_from_cfg, merge_
 FILES = ["mfrl/sac/dm_control/pn.py", "mfrl/sac/maniskill/pn.py", "mfrl/drq/maniskill/pn_jitter.py",
          "mfrl/drq/maniskill/pn_rot.py", "mfrl/drq/dm_control/pn_jitter.py", "mfrl/drq/dm_control/pn_rot.py",
          "mfrl/drq/maniskill/pn_shift.py", "mfrl/drq/dm_control/pn_shift.py",
-         "mfrl/drq/maniskill/pn_dropout.py", "mfrl/drq/dm_control/pn_dropout.py"]
+         "mfrl/drq/maniskill/pn_dropout.py", "mfrl/drq/dm_control/pn_dropout.py",
+         "mfrl/drq/maniskill/pn_colorjitter.py", "mfrl/drq/dm_control/pn_colorjitter.py"]
 
 
 def _plain(x):

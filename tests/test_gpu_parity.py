@@ -433,20 +433,62 @@ def _engine_from_golden(g, precision="fp32"):
     hp = HyperParams(algo=m["algo"], gamma=m["gamma"], reward_scale=m["reward_scale"], num_aug=m["num_aug"],
                      aug=m["aug"] or None, aug_lo=m["aug_lo"], aug_hi=m["aug_hi"], tau=m["tau"],
                      actor_update_interval=m["actor_update_interval"],
-                     target_update_interval=m["target_update_interval"], target_entropy=m["target_entropy"])
+                     target_update_interval=m["target_update_interval"], target_entropy=m["target_entropy"],
+                     aug_color=tuple(m.get(f"cj_{c}", 0.0) for c in "bcsh"))
     eng = UpdateEngine(spec, hp, batch_size=m["B"], precision=precision)
     eng.load_params(init)
     eng.prime_alpha()
     return eng, m
 
 
-@pytest.mark.parametrize("name", ["sac_dmc_small", "drq_jitter_small", "drq_rot_small", "drq_shift_small", "drq_downsample_small"])
+def test_color_jitter_points_bit_exact_vs_torchvision(L):
+    """ColorJitterPoints (pcd_aug.py:269-303): every op order and a spread of factors, uint8 in / uint8 out, against
+    torchvision's own adjust_* functions (the oracle's aug_colorjitter) -- bit-exact, including hue wrap-around, grey
+    points (max == min) and saturated colours."""
+    import itertools
+
+    rs = np.random.RandomState(0)
+    B, N = 5, 333
+    rgb = rs.randint(0, 256, size=(B, 3, N)).astype(np.uint8)
+    rgb[0, :, :40] = rgb[0, :1, :40]                  # grey points
+    rgb[1, :, :20] = np.array([255, 0, 0])[:, None]   # saturated primaries
+    rgb[1, :, 20:40] = 0
+    rgb[2, :, :10] = 255
+    t = torch.from_numpy(rgb)
+    out = torch.empty(B, 3, N, dtype=torch.uint8, device="cuda")
+    factors = [(0.6, 1.4, 0.6, -0.5), (1.4, 0.6, 1.4, 0.5), (1.0, 1.0, 1.0, 0.0), (0.83, 1.17, 0.0, 0.251), (1.37, 0.71, 2.0, -0.013)]
+    for i, order in enumerate(itertools.permutations(range(4))):
+        f = factors[i % len(factors)]
+        params = torch.tensor([float(o) for o in order] + list(f), dtype=torch.float32)
+        ref = O.aug_colorjitter(t, params.double())
+        L.color_jitter_points(t.cuda(), B, N, params.cuda(), 0.4, 0.4, 0.4, 0.5, 0, None, 0, out, sp())
+        assert torch.equal(out.cpu(), ref), (order, f, int((out.cpu() != ref).sum()))
+    # Philox mode: one parameter set per call (all clouds share it), deterministic in (seed, counter), new per counter
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    same = torch.from_numpy(np.repeat(rgb[:1], B, axis=0)).cuda()
+    L.color_jitter_points(same, B, N, None, 0.4, 0.4, 0.4, 0.5, 9, cnt, 0, out, sp())
+    assert all(torch.equal(out[0], out[b]) for b in range(1, B))
+    first = out.clone()
+    L.color_jitter_points(same, B, N, None, 0.4, 0.4, 0.4, 0.5, 9, cnt, 0, out, sp())
+    assert torch.equal(first, out)
+    cnt += 1
+    L.color_jitter_points(same, B, N, None, 0.4, 0.4, 0.4, 0.5, 9, cnt, 0, out, sp())
+    assert not torch.equal(first, out)
+
+
+def _noise_to_device(tree):
+    noise = {k: v.cuda() for k, v in _t(tree).items()}
+    return {k: (v.reshape(-1) if k.startswith("angle") else v.float() if k.startswith("cj_") else v) for k, v in noise.items()}
+
+
+@pytest.mark.parametrize("name", ["sac_dmc_small", "drq_jitter_small", "drq_rot_small", "drq_shift_small", "drq_downsample_small",
+                                  "drq_colorjitter_small"])
 def test_update_matches_reference_fp32(name):
     g = load_golden(name)
     eng, m = _engine_from_golden(g)
     eng.upload_batch(g["batch"])
     for u in range(1, m["n_updates"] + 1):
-        noise = {k: v.cuda() for k, v in _t(g[f"noise{u}"]).items()}
+        noise = _noise_to_device(g[f"noise{u}"])
         if "angle_obs" in noise:
             noise = {k: (v.reshape(-1) if k.startswith("angle") else v) for k, v in noise.items()}
         eng.update(u, noise)
@@ -467,13 +509,13 @@ def test_update_matches_reference_fp32(name):
             assert float((delta - delta_ref).abs().max()) <= 2.1e-3 * u, (u, key)
 
 
-@pytest.mark.parametrize("name", ["sac_dmc_small", "drq_jitter_small", "drq_shift_small", "drq_downsample_small"])
+@pytest.mark.parametrize("name", ["sac_dmc_small", "drq_jitter_small", "drq_shift_small", "drq_downsample_small", "drq_colorjitter_small"])
 def test_update_bf16_within_tolerance(name):
     """bf16 tensor-core forward inside the full update: logged scalars within 2e-2 of the reference."""
     g = load_golden(name)
     eng, m = _engine_from_golden(g, precision="bf16")
     eng.upload_batch(g["batch"])
-    noise = {k: v.cuda() for k, v in _t(g["noise1"]).items()}
+    noise = _noise_to_device(g["noise1"])
     eng.update(1, noise)
     ret = eng.read_scalars(1)
     ref = {f"{a}/{b}": float(v) for a, sub in g["ret1"].items() for b, v in sub.items()}

@@ -45,7 +45,8 @@ def test_argmax_ties_pick_smallest_index():
     assert (idx < q).all()
 
 
-@pytest.mark.parametrize("name", ["sac_dmc_small", "drq_jitter_small", "drq_rot_small", "drq_shift_small", "drq_downsample_small"])
+@pytest.mark.parametrize("name", ["sac_dmc_small", "drq_jitter_small", "drq_rot_small", "drq_shift_small", "drq_downsample_small",
+                                  "drq_colorjitter_small"])
 def test_update_matches_reference(name):
     g = load_golden(name)
     m = {k: v.item() for k, v in g["meta"].items()}
