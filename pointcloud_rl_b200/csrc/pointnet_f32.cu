@@ -311,10 +311,37 @@ int64_t pcrl_pointnet_fwd_f32_workspace(int clouds, int NP, int c1, int c2, int 
   return (int64_t)clouds * NP * (c1 + c2 + c3) * sizeof(float);
 }
 
+static int pointnet_fwd_chain(const float* xf, int R, int N, int NP, int CP, int C, const float* w0, const float* b0,
+                              const float* w1, const float* g1, const float* be1, const float* w2, const float* g2,
+                              const float* be2, int c1, int c2, int c3, float ln_eps, float* pooled, int32_t* argmax,
+                              void* workspace, int64_t workspace_bytes, int tf32, void* stream);
+
 int pcrl_pointnet_fwd_f32(const float* xf, int R, int N, int NP, int CP, int C, const float* w0, const float* b0,
                           const float* w1, const float* g1, const float* be1, const float* w2, const float* g2,
                           const float* be2, int c1, int c2, int c3, float ln_eps, float* pooled, int32_t* argmax,
                           void* workspace, int64_t workspace_bytes, void* stream) {
+  return pointnet_fwd_chain(xf, R, N, NP, CP, C, w0, b0, w1, g1, be1, w2, g2, be2, c1, c2, c3, ln_eps, pooled, argmax,
+                            workspace, workspace_bytes, 0, stream);
+}
+
+int pcrl_pointnet_fwd_tf32(const float* xf, int R, int N, int NP, int CP, int C, const float* w0, const float* b0,
+                           const float* w1, const float* g1, const float* be1, const float* w2, const float* g2,
+                           const float* be2, int c1, int c2, int c3, float ln_eps, float* pooled, int32_t* argmax,
+                           void* workspace, int64_t workspace_bytes, void* stream) {
+  if (c1 % 4 || c2 % 4 || c1 < 8 || c2 < 8) {
+    set_error("pcrl_pointnet_fwd_tf32: widths (%d,%d,%d) need c1, c2 multiples of 4 (TMA row pitch) and >= 8", c1, c2, c3);
+    return PCRL_EUNSUPPORTED;
+  }
+  return pointnet_fwd_chain(xf, R, N, NP, CP, C, w0, b0, w1, g1, be1, w2, g2, be2, c1, c2, c3, ln_eps, pooled, argmax,
+                            workspace, workspace_bytes, 1, stream);
+}
+
+// tf32 = 1: layers 1 and 2 (99.3 % of the FLOPs) run on the TF32 tcgen05 GEMM straight from the fp32 activations; layer 0
+// (K = C <= 12), LayerNorm statistics, the max / argmax stay exact fp32, and the 64-bit (value, ~index) keys are untruncated.
+static int pointnet_fwd_chain(const float* xf, int R, int N, int NP, int CP, int C, const float* w0, const float* b0,
+                              const float* w1, const float* g1, const float* be1, const float* w2, const float* g2,
+                              const float* be2, int c1, int c2, int c3, float ln_eps, float* pooled, int32_t* argmax,
+                              void* workspace, int64_t workspace_bytes, int tf32, void* stream) {
   PCRL_CHECK_ARG(xf && w0 && b0 && w1 && g1 && be1 && w2 && g2 && be2 && pooled && workspace);
   PCRL_CHECK_ARG(R >= 0 && N > 0 && NP >= N && NP % 128 == 0 && C <= CP);
   cudaStream_t st = as_stream(stream);
@@ -332,10 +359,10 @@ int pcrl_pointnet_fwd_f32(const float* xf, int R, int N, int NP, int CP, int C, 
     // h0 = relu(x W0^T + b0)                     (conv0 + ReLU; no norm: ignore_first_ln)
     if ((rc = gemm_nt(x, CP, w0, C, b0, 1, h0, c1, P, C, c1, nullptr, st))) return rc;
     // h1 = relu(LN(h0 W1^T))
-    if ((rc = gemm_nt(h0, c1, w1, c1, nullptr, 0, h1, c2, P, c1, c2, nullptr, st))) return rc;
+    if ((rc = gemm_nt(h0, c1, w1, c1, nullptr, 0, h1, c2, P, c1, c2, nullptr, st, tf32))) return rc;
     if ((rc = launch_ln_rows(h1, c2, g1, be1, h1, c2, nullptr, nullptr, P, c2, ln_eps, 1, nullptr, st))) return rc;
     // h2 = relu(LN(h1 W2^T))
-    if ((rc = gemm_nt(h1, c2, w2, c2, nullptr, 0, h2, c3, P, c2, c3, nullptr, st))) return rc;
+    if ((rc = gemm_nt(h1, c2, w2, c2, nullptr, 0, h2, c3, P, c2, c3, nullptr, st, tf32))) return rc;
     if ((rc = launch_ln_rows(h2, c3, g2, be2, h2, c3, nullptr, nullptr, P, c3, ln_eps, 1, nullptr, st))) return rc;
     dim3 grid((unsigned)cdiv(c3, 256), (unsigned)rows);
     maxpool_points_kernel<<<grid, 256, 0, st>>>(h2, rows, N, NP, c3, pooled + (int64_t)r0 * c3,

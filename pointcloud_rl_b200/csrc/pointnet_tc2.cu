@@ -614,25 +614,37 @@ pack_weights2_kernel(const float* __restrict__ w0, const float* __restrict__ b0,
     const int e = i - n0 - n1, n = e / c2, k = e % c2;
     const float v = w2[e] - m2[k];
     *reinterpret_cast<__nv_bfloat16*>(out + W.w2 + img_off(n, k, c2)) = __float2bfloat16(g2[n] >= 0.f ? v : -v);
-  } else if (i < n0 + n1 + n2 + n3) {
-    // Gram matrix of the centred, bf16-ROUNDED layer-2 weights (what the tensor core multiplies by): fp32 accumulate,
-    // four independent chains over the c3 rows
-    const int e = i - n0 - n1 - n2, k = e / c2, kk = e % c2;
-    const float mk = m2[k], mkk = m2[kk];
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    for (int n = 0; n < c3; n += 4) {
-      s0 = fmaf(bf16_round(w2[n * c2 + k] - mk), bf16_round(w2[n * c2 + kk] - mkk), s0);
-      s1 = fmaf(bf16_round(w2[(n + 1) * c2 + k] - mk), bf16_round(w2[(n + 1) * c2 + kk] - mkk), s1);
-      s2 = fmaf(bf16_round(w2[(n + 2) * c2 + k] - mk), bf16_round(w2[(n + 2) * c2 + kk] - mkk), s2);
-      s3 = fmaf(bf16_round(w2[(n + 3) * c2 + k] - mk), bf16_round(w2[(n + 3) * c2 + kk] - mkk), s3);
-    }
-    *reinterpret_cast<__nv_bfloat16*>(out + W.gc + img_off(k, kk, c2)) = __float2bfloat16((s0 + s1) + (s2 + s3));
-  } else if (i < n0 + n1 + n2 + n3 + n4) {
+  } else if (i >= n0 + n1 + n2 + n3 && i < n0 + n1 + n2 + n3 + n4) {
     const int e = i - n0 - n1 - n2 - n3;
     if (e < c2) reinterpret_cast<float*>(out + W.prm1)[e] = g1[e];
     else if (e < 2 * c2) reinterpret_cast<float*>(out + W.prm1)[e] = be1[e - c2];
     else if (e < 2 * c2 + c3) reinterpret_cast<float*>(out + W.prm2)[e - 2 * c2] = g2[e - 2 * c2];
     else reinterpret_cast<float*>(out + W.prm2)[e - 2 * c2] = be2[e - 2 * c2 - c3];
+  }
+}
+
+// Gram matrix Gc = W2c^T W2c of the centred, bf16-ROUNDED layer-2 weights (what the tensor core multiplies by), fp32
+// accumulate.  One block = 32 consecutive outputs (k, kk .. kk+31) x 8 row groups: every thread sums c3/8 rows (the kk
+// loads coalesce, the k column is a broadcast) and the partials meet in shared memory.  ~2 us, where one thread per
+// output looping over all c3 rows is latency-bound at ~20 us.
+__global__ void __launch_bounds__(256)
+gram_kernel(const float* __restrict__ w2, const float* __restrict__ m2, int c2, int c3, char* __restrict__ gc_img) {
+  __shared__ float part[8][33];
+  const int o = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + o, k = e / c2, kk = e % c2;
+  const float mk = m2[k], mkk = m2[kk];
+  float s0 = 0.f, s1 = 0.f;
+  for (int n = g; n < c3; n += 16) {
+    s0 = fmaf(bf16_round(w2[n * c2 + k] - mk), bf16_round(w2[n * c2 + kk] - mkk), s0);
+    if (n + 8 < c3) s1 = fmaf(bf16_round(w2[(n + 8) * c2 + k] - mk), bf16_round(w2[(n + 8) * c2 + kk] - mkk), s1);
+  }
+  part[g][o] = s0 + s1;
+  __syncthreads();
+  if (g == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][o];
+    *reinterpret_cast<__nv_bfloat16*>(gc_img + img_off(k, kk, c2)) = __float2bfloat16(t);
   }
 }
 
@@ -649,6 +661,10 @@ int pack(const float* w0, const float* b0, const float* w1, const float* g1, con
   PCRL_CHECK_LAUNCH();
   pack_weights2_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(w0, b0, w1, g1, be1, w2, g2, be2, C, c1, c2, c3, rgb_u8,
                                                                 (char*)wpack2);
+  PCRL_CHECK_LAUNCH();
+  const Wpack2 W = make_wpack2(c1, c2, c3);
+  gram_kernel<<<(unsigned)(c2 * c2 / 32), 256, 0, st>>>(w2, reinterpret_cast<const float*>((char*)wpack2 + W.cm) + c1, c2, c3,
+                                                       (char*)wpack2 + W.gc);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }

@@ -147,16 +147,20 @@ class ParamLayout:
 class UpdateEngine:
     def __init__(self, spec: PathSpec, hp: HyperParams, batch_size: int, device="cuda:0", precision="fp32",
                  seed: int = 0, fwd_chunk_clouds: int = 64):
-        assert precision in ("fp32", "bf16")
+        assert precision in ("fp32", "tf32", "bf16")
         self.L = lib()
         self.spec, self.hp, self.B = spec, hp, int(batch_size)
         self.k = hp.num_aug if hp.algo == "drq" else 1
         self.R = self.B * self.k
         self.device = torch.device(device)
         self.precision = precision
-        # "bf16" = the fast mode: bf16 tcgen05 PointNet forward + TF32 tcgen05 GEMMs for the MLP heads and the
-        # compacted backward; "fp32" = the parity mode: every product on the exact-fp32 FFMA kernels
-        self.tf32 = 1 if precision == "bf16" else 0
+        # "bf16" = the fast mode: fused bf16 tcgen05 PointNet forward + TF32 tcgen05 GEMMs for the MLP heads and the
+        # compacted backward; "tf32" = the reference-precision tier on tensor cores: every GEMM of the path (PointNet
+        # layers 1-2 included) on the TF32 tcgen05 kernel, all statistics / max / argmax exact fp32; "fp32" = the
+        # parity mode: every product on the exact-fp32 FFMA kernels
+        self.tf32 = 1 if precision in ("bf16", "tf32") else 0
+        if precision == "tf32":
+            fwd_chunk_clouds = min(fwd_chunk_clouds, 32)  # a chunk's activations (h0|h1|h2) stay inside the 126 MB L2
         self.seed = int(seed)
         self.layout = ParamLayout(spec)
         dev = self.device
@@ -430,13 +434,15 @@ class UpdateEngine:
                 self.L.pointnet_fwd_bf16(w[f"xh_{name}"], rows, sp.n_points, sp.NP, w["wpack"], c1, c2, c3, sp.ln_eps,
                                          w[f"pool_keys_{name}"], w[f"pooled_{name}"], argmax, st)
         else:
-            self.L.pointnet_fwd_f32(w[f"xf_{name}"], rows, sp.n_points, sp.NP, sp.CP, sp.C, p["pn.w0"], p["pn.b0"],
-                                    p["pn.w1"], p["pn.g1"], p["pn.be1"], p["pn.w2"], p["pn.g2"], p["pn.be2"], c1, c2,
-                                    c3, sp.ln_eps, w[f"pooled_{name}"], argmax,
-                                    w["scratch_next" if name == "next" else "scratch"], self.fwd_ws_bytes, st)
+            fwd = self.L.pointnet_fwd_tf32 if self.precision == "tf32" else self.L.pointnet_fwd_f32
+            fwd(w[f"xf_{name}"], rows, sp.n_points, sp.NP, sp.CP, sp.C, p["pn.w0"], p["pn.b0"], p["pn.w1"], p["pn.g1"],
+                p["pn.be1"], p["pn.w2"], p["pn.g2"], p["pn.be2"], c1, c2, c3, sp.ln_eps, w[f"pooled_{name}"], argmax,
+                w["scratch_next" if name == "next" else "scratch"], self.fwd_ws_bytes, st)
 
     def dominant_kernel_name(self):
-        return "pointnet_fwd_tc_kernel" if self.precision == "bf16" else "pointnet_fwd_f32 chain"
+        return {"bf16": "pointnet_fwd_tc2_kernel (fused tcgen05 forward)",
+                "tf32": "pointnet_fwd_tf32 chain (TF32 tcgen05 GEMMs + LayerNorm + max-pool)",
+                "fp32": "pointnet_fwd_f32 chain (exact FFMA)"}[self.precision]
 
     def _pack_weights(self, st, which=3):
         """bf16 path: re-pack the (just updated) PointNet weights into the MMA-ready images.  which: 1 = the image the

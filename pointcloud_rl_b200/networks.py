@@ -159,7 +159,7 @@ class KernelRunner:
 
     def __init__(self, precision="bf16", seed=0):
         self.precision = precision
-        self.tf32 = 1 if precision == "bf16" else 0
+        self.tf32 = 1 if precision in ("bf16", "tf32") else 0
         self.seed = seed
         self.L = lib()
         self._ws = {}
@@ -183,7 +183,7 @@ class KernelRunner:
                 ws["wpack"] = torch.zeros(int(L.pointnet_wpack_bytes(c1, c2, c3)), dtype=torch.uint8, device=device)
                 ws["keys"] = torch.zeros(B * c3, dtype=torch.int64, device=device)
             else:
-                chunk = max(1, min(B, 64))
+                chunk = max(1, min(B, 32 if self.precision == "tf32" else 64))
                 ws["fwd_bytes"] = int(L.pointnet_fwd_f32_workspace(chunk, spec.NP, c1, c2, c3))
                 ws["scratch"] = torch.zeros(ws["fwd_bytes"], dtype=torch.uint8, device=device)
             self._ws[key] = ws
@@ -219,9 +219,10 @@ class KernelRunner:
             L.pointnet_fwd_bf16(ws["xh"], B, spec.n_points, spec.NP, ws["wpack"], c1, c2, c3, spec.ln_eps, ws["keys"],
                                 ws["pooled"], None, st)
         else:
-            L.pointnet_fwd_f32(ws["xf"], B, spec.n_points, spec.NP, spec.CP, spec.C, p["pn.w0"], p["pn.b0"], p["pn.w1"],
-                               p["pn.g1"], p["pn.be1"], p["pn.w2"], p["pn.g2"], p["pn.be2"], c1, c2, c3, spec.ln_eps,
-                               ws["pooled"], None, ws["scratch"], ws["fwd_bytes"], st)
+            fwd = L.pointnet_fwd_tf32 if self.precision == "tf32" else L.pointnet_fwd_f32
+            fwd(ws["xf"], B, spec.n_points, spec.NP, spec.CP, spec.C, p["pn.w0"], p["pn.b0"], p["pn.w1"], p["pn.g1"],
+                p["pn.be1"], p["pn.w2"], p["pn.g2"], p["pn.be2"], c1, c2, c3, spec.ln_eps, ws["pooled"], None,
+                ws["scratch"], ws["fwd_bytes"], st)
         D = spec.out_dim
         if out is None:
             out = torch.empty(B, D, dtype=torch.float32, device=device)

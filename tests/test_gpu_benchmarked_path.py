@@ -37,7 +37,7 @@ def grads_of(eng, keys):
     return {k: eng.g[k].detach().clone().cpu() for k in keys}
 
 
-def oracle_with_engine_selection(eng, state_before, batch, updates, hp_o, noise):
+def oracle_with_engine_selection(eng, state_before, batch, updates, hp_o, noise, tol=REL_BF16):
     """bf16 tier: the oracle's gradients with the max-pool selection the kernel made (see pointnet_forward's
     idx_override), after checking the selection itself: every selected point's TRUE (fp32) feature is within the
     bf16 tolerance of the channel's true maximum."""
@@ -45,12 +45,12 @@ def oracle_with_engine_selection(eng, state_before, batch, updates, hp_o, noise)
     cap = {}
     O.update(copy.deepcopy(state_before), batch, updates, hp_o, noise, capture=cap, idx_override=idx)
     true_max, picked = cap["h_obs_max"], cap["pooled_obs"]
-    assert float((true_max - picked).max()) <= REL_BF16 * float(true_max.max()), "selected a point that is not a near-tie"
+    assert float((true_max - picked).max()) <= tol * float(true_max.max()), "selected a point that is not a near-tie"
     assert float((true_max - picked).min()) >= 0.0
     return cap
 
 
-def check_update_tensors(eng, cap, ref, got, updates, hp, tol, D, cap_sel=None, pn_tol=None):
+def check_update_tensors(eng, cap, ref, got, updates, hp, tol, D, cap_sel=None, pn_tol=None, grad_tol=None):
     """features / Q-values / gradients / logged scalars of ONE update against the oracle's captured tensors.
     cap_sel (bf16 tier): oracle run with the kernel's max-pool selection -- the PointNet tensors' gradients are
     compared against it (one flipped near-tie moves a channel's whole gradient to another point), everything else,
@@ -61,6 +61,7 @@ def check_update_tensors(eng, cap, ref, got, updates, hp, tol, D, cap_sel=None, 
     average out and the stated 2e-2 holds (test_full_size_update_matches_oracle); the 96-point golden fixtures have
     ~10^3 active points, so they are bounded at 0.15 there."""
     pn_tol = tol if pn_tol is None else pn_tol
+    grad_tol = tol if grad_tol is None else grad_tol  # MLP-head gradient tensors and the gradient-norm scalars
     w = eng.w
     actor_step = updates % hp.actor_update_interval == 0
     errs = {"q": rel_err(w["q_obs"], cap["q"]), "f_next": rel_err(w["cat_next"][:, :D], cap["f_next"]),
@@ -74,8 +75,9 @@ def check_update_tensors(eng, cap, ref, got, updates, hp, tol, D, cap_sel=None, 
         if big[k] > 1e-3 * gmax:  # tensors whose gradient is rounding noise next to the others are covered by the norm below
             src = cap_sel if cap_sel is not None else cap
             errs[f"dL/d{k}"] = rel_err(g, src["critic_grads"][k])
+    src = cap_sel if cap_sel is not None else cap
     errs["critic_grad_all"] = rel_err(torch.cat([g.flatten() for g in cg.values()]),
-                                      torch.cat([cap["critic_grads"][k].flatten() for k in cg]))
+                                      torch.cat([src["critic_grads"][k].flatten() for k in cg]))
     if actor_step:
         name = "pi" if eng.k > 1 else "obs"
         errs["f_pi"] = rel_err(w[f"cat_{name}"][:eng.B, :D], cap["f_pi"])
@@ -83,11 +85,17 @@ def check_update_tensors(eng, cap, ref, got, updates, hp, tol, D, cap_sel=None, 
         ag = grads_of(eng, O.actor_keys())
         errs["actor_grad_all"] = rel_err(torch.cat([g.flatten() for g in ag.values()]),
                                          torch.cat([cap["actor_grads"][k].flatten() for k in ag]))
-    bad = {k: v for k, v in errs.items() if not v < (pn_tol if k.startswith("dL/dpn.") else tol)}
+    def lim(k):
+        if k.startswith("dL/dpn.") or k == "critic_grad_all":
+            return pn_tol
+        return grad_tol if (k.startswith("dL/d") or k == "actor_grad_all") else tol
+
+    bad = {k: v for k, v in errs.items() if not v < lim(k)}
     assert not bad, (updates, {k: round(v, 4) for k, v in sorted(bad.items(), key=lambda kv: -kv[1])},
                      {k: round(v, 4) for k, v in errs.items()})
     for key, val in ref.items():
-        assert got[key] == pytest.approx(val, rel=tol, abs=tol), (updates, key, got[key], val)
+        t = grad_tol if key.endswith("_grad") else tol
+        assert got[key] == pytest.approx(val, rel=t, abs=t), (updates, key, got[key], val)
     return errs
 
 
@@ -104,7 +112,7 @@ def _noise_dev(g, u):
 
 
 @pytest.mark.parametrize("graph", [True, False])
-@pytest.mark.parametrize("precision,tol", [("bf16", REL_BF16), ("fp32", REL_FP32)])
+@pytest.mark.parametrize("precision,tol", [("bf16", REL_BF16), ("tf32", REL_FP32), ("fp32", REL_FP32)])
 @pytest.mark.parametrize("name", ["drq_jitter_small", "sac_dmc_small", "drq_rot_small", "drq_colorjitter_small"])
 def test_each_update_matches_oracle_tensors(name, precision, tol, graph):
     """Updates 1-4 (critic-only and actor/alpha/Polyak steps), eager and CUDA-graph replay with injected noise: every
@@ -129,8 +137,10 @@ def test_each_update_matches_oracle_tensors(name, precision, tol, graph):
         else:
             eng.update(u, _noise_dev(g, u))
         got = eng.read_scalars(u)
-        cap_sel = oracle_with_engine_selection(eng, before, g["batch"], u, hp, noise_cpu) if precision == "bf16" else None
-        check_update_tensors(eng, cap, ref, got, u, eng.hp, tol, D, cap_sel, pn_tol=0.15 if precision == "bf16" else None)
+        cap_sel = oracle_with_engine_selection(eng, before, g["batch"], u, hp, noise_cpu, tol) if precision != "fp32" else None
+        # reduced-precision tiers at toy size: see check_update_tensors (mask / selection flips do not average out)
+        extra = {"bf16": dict(pn_tol=0.15), "tf32": dict(pn_tol=0.05, grad_tol=5e-3), "fp32": {}}[precision]
+        check_update_tensors(eng, cap, ref, got, u, eng.hp, tol, D, cap_sel, **extra)
         if precision == "fp32":
             after = eng.export_params()
             for key in ("pn.w1", "pn.g2", "q0.w1", "actor.w2", "tq1.w0", "log_alpha"):
@@ -197,7 +207,7 @@ FULL = {
 }
 
 
-@pytest.mark.parametrize("precision,tol", [("bf16", REL_BF16), ("fp32", REL_FP32)])
+@pytest.mark.parametrize("precision,tol", [("bf16", REL_BF16), ("tf32", REL_FP32), ("fp32", REL_FP32)])
 @pytest.mark.parametrize("cfg", sorted(FULL))
 def test_full_size_update_matches_oracle(cfg, precision, tol):
     """The BASELINE configurations at FULL size (hidden 1024: every MLP layer takes the cluster split-K GEMM path the
@@ -232,13 +242,17 @@ def test_full_size_update_matches_oracle(cfg, precision, tol):
     before = copy.deepcopy(state)
     cap = {}
     ref = O.update(state, batch, 2, hp_o, noise, capture=cap)
-    step = eng.update_graphed if precision == "bf16" else eng.update
+    step = eng.update if precision == "fp32" else eng.update_graphed
     step(2, {k: v.cuda() for k, v in noise.items()})
     got = eng.read_scalars(2)
-    cap_sel = oracle_with_engine_selection(eng, before, batch, 2, hp_o, noise) if precision == "bf16" else None
-    errs = check_update_tensors(eng, cap, ref, got, 2, hp, tol, c["D"], cap_sel)
+    cap_sel = oracle_with_engine_selection(eng, before, batch, 2, hp_o, noise, tol) if precision != "fp32" else None
+    # TF32 tier: features / Q-values / scalars at 1e-3; its gradients carry TF32 operand truncation through the backward
+    # GEMMs and the LayerNorm backward's cancellations: 5e-3
+    extra = dict(pn_tol=5e-3, grad_tol=5e-3) if precision == "tf32" else {}
+    errs = check_update_tensors(eng, cap, ref, got, 2, hp, tol, c["D"], cap_sel, **extra)
     print(cfg, precision, {k: f"{v:.2e}" for k, v in errs.items()})
-    if precision == "fp32":
-        # exact tier: the argmax indices agree except between near-ties
-        idx = eng.w["argmax_obs"].cpu().long()
-        assert float((idx != cap["idx_obs"]).float().mean()) < 5e-3
+    idx = eng.w["argmax_obs"].cpu().long()
+    mism = float((idx != cap["idx_obs"]).float().mean())
+    print(cfg, precision, "argmax mismatch fraction", mism)
+    if precision == "fp32":  # exact tier: the argmax indices agree except between near-ties
+        assert mism < 5e-3
