@@ -119,6 +119,7 @@ int pcrl_pointnet_fwd_f32(const float* xf, int R, int N, int NP, int CP, int C, 
 /* Reference-precision tier on the tensor cores: same contract as pcrl_pointnet_fwd_f32, layers 1 and 2 on the TF32 tcgen05
  * GEMM (10-bit mantissa operands, fp32 accumulate), everything else exact fp32 (layer 0, LayerNorm, max / argmax with
  * untruncated 64-bit keys).  Tolerance class: 1e-3 relative; argmax equal up to near-ties. */
+int64_t pcrl_pointnet_fwd_tf32_workspace(int clouds, int NP, int c1, int c2, int c3);
 int pcrl_pointnet_fwd_tf32(const float* xf, int R, int N, int NP, int CP, int C, const float* w0, const float* b0,
                            const float* w1, const float* g1, const float* be1, const float* w2, const float* g2,
                            const float* be2, int c1, int c2, int c3, float ln_eps, float* pooled, int32_t* argmax,

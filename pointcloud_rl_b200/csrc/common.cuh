@@ -63,6 +63,13 @@ __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
   return make_float2(r * c, r * s);
 }
 
+// fp32 -> nearest TF32 (10-bit mantissa, ties away), kept in an fp32 container: the TF32 tensor-core path ignores the low
+// 13 mantissa bits of its operands, i.e. TRUNCATES; producers that feed it round instead (half the error, no bias)
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -88,7 +95,7 @@ struct GemmArgs {
   int64_t ldc;
   int M, N, K;
   const float* bias;  // per column j, may be null
-  int relu;
+  int relu;           // bit 0: ReLU; bit 1 (FFMA kernel only): round the stored value to TF32 (it feeds a TF32 GEMM)
   int accumulate;     // atomicAdd into C (required when split_k > 1)
   int split_k;
   const int* m_dev;   // if set, rows i >= *m_dev are skipped (M rows)

@@ -43,7 +43,7 @@ int launch_gemm(const GemmArgs& g, int tf32, cudaStream_t st) {
     t.A = g.A; t.lda = t.a_mn ? g.a_sl : g.a_si;
     t.b_mn = (g.b_sl == 1) ? 0 : 1;
     t.B = g.B; t.ldb = t.b_mn ? g.b_sl : g.b_sj;
-    t.bias = g.bias; t.C = g.C; t.ldc = g.ldc; t.M = g.M; t.N = g.N; t.K = g.K; t.relu = g.relu;
+    t.bias = g.bias; t.C = g.C; t.ldc = g.ldc; t.M = g.M; t.N = g.N; t.K = g.K; t.relu = g.relu & 1;
     t.split_k = g.split_k;
     t.mode = g.accumulate ? (g.split_k > 1 ? 2 : 1) : 0;
     t.k_dev = g.k_dev; t.m_dev = g.m_dev; t.mask = g.mask; t.ldmask = g.ldmask; t.bn_hint = g.bn_hint;

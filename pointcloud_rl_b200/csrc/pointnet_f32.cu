@@ -34,6 +34,72 @@ __global__ void __launch_bounds__(256) maxpool_points_kernel(const float* __rest
   if (argmax) argmax[(int64_t)r * c3 + c] = bi;
 }
 
+// LayerNorm + ReLU + max over the points, fused (the last layer of the unfused fp32 / TF32 chains): y [rows, NP, c3] is the
+// raw layer-2 GEMM output; nothing is written back except the packed per-(cloud, channel) maximum, so the 2 x c3 floats
+// per point of a separate LN pass + max-pool pass never move.  Same arithmetic, in the same order, as ln_rows_kernel
+// followed by maxpool_points_kernel (a warp per point, lane l owns channels l, l+32, ...).
+// grid (slices, rows): block (r, s) takes points n = s*warps + w, step slices*warps; partial maxima meet in a 64-bit
+// atomicMax on (float bits << 32 | ~index): values are >= 0 after the ReLU, so bit order is value order and ties
+// resolve to the smallest index (torch.max semantics).  keys must be zero on entry; finalize_keys_kernel unpacks.
+template <int VPL>
+__global__ void __launch_bounds__(256)
+ln_relu_maxpool_kernel(const float* __restrict__ y, int N, int NP, int c3, const float* __restrict__ g,
+                       const float* __restrict__ b, float eps, unsigned long long* __restrict__ keys) {
+  const int r = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warps = blockDim.x >> 5;
+  const float inv_d = 1.0f / (float)c3;
+  float gv[VPL], bv[VPL], best[VPL];
+  int bi[VPL];
+#pragma unroll
+  for (int q = 0; q < VPL; ++q) {
+    gv[q] = g[lane + 32 * q];
+    bv[q] = b[lane + 32 * q];
+    best[q] = -1.f;
+    bi[q] = 0;
+  }
+  for (int n = blockIdx.x * warps + warp; n < N; n += gridDim.x * warps) {
+    const float* xr = y + ((int64_t)r * NP + n) * c3;
+    float x[VPL];
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) {
+      x[q] = xr[lane + 32 * q];
+      s += x[q];
+    }
+    const float mean = warp_sum(s) * inv_d;
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) {
+      const float d = x[q] - mean;
+      v = fmaf(d, d, v);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(v) * inv_d + eps);
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) {
+      const float xh = (x[q] - mean) * rstd;
+      const float o = fmaxf(fmaf(xh, gv[q], bv[q]), 0.f);
+      if (o > best[q]) {  // points ascend within a warp: strict > keeps the smallest index
+        best[q] = o;
+        bi[q] = n;
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < VPL; ++q)
+    if (best[q] >= 0.f)
+      atomicMax(keys + (int64_t)r * c3 + lane + 32 * q,
+                ((unsigned long long)__float_as_uint(best[q]) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)bi[q]));
+}
+
+__global__ void finalize_keys_kernel(unsigned long long* __restrict__ keys, int64_t n, float* __restrict__ pooled,
+                                     int32_t* __restrict__ argmax) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long k = keys[i];
+  pooled[i] = __uint_as_float((uint32_t)(k >> 32));
+  if (argmax) argmax[i] = (int32_t)(0xFFFFFFFFu - (uint32_t)k);
+}
+
 // ---- sparse backward helpers -----------------------------------------------------------------
 
 // A point carries gradient when it won the max for some channel (r, c) with pooled > 0 (ReLU passes) and
@@ -310,6 +376,9 @@ extern "C" {
 int64_t pcrl_pointnet_fwd_f32_workspace(int clouds, int NP, int c1, int c2, int c3) {
   return (int64_t)clouds * NP * (c1 + c2 + c3) * sizeof(float);
 }
+int64_t pcrl_pointnet_fwd_tf32_workspace(int clouds, int NP, int c1, int c2, int c3) {
+  return pcrl_pointnet_fwd_f32_workspace(clouds, NP, c1, c2, c3) + align_up((int64_t)(c2 * c1 + c3 * c2) * 4, 256);
+}
 
 static int pointnet_fwd_chain(const float* xf, int R, int N, int NP, int CP, int C, const float* w0, const float* b0,
                               const float* w1, const float* g1, const float* be1, const float* w2, const float* g2,
@@ -336,6 +405,11 @@ int pcrl_pointnet_fwd_tf32(const float* xf, int R, int N, int NP, int CP, int C,
                             workspace, workspace_bytes, 1, stream);
 }
 
+__global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = round_tf32(src[i]);
+}
+
 // tf32 = 1: layers 1 and 2 (99.3 % of the FLOPs) run on the TF32 tcgen05 GEMM straight from the fp32 activations; layer 0
 // (K = C <= 12), LayerNorm statistics, the max / argmax stay exact fp32, and the 64-bit (value, ~index) keys are untruncated.
 static int pointnet_fwd_chain(const float* xf, int R, int N, int NP, int CP, int C, const float* w0, const float* b0,
@@ -346,8 +420,23 @@ static int pointnet_fwd_chain(const float* xf, int R, int N, int NP, int CP, int
   PCRL_CHECK_ARG(R >= 0 && N > 0 && NP >= N && NP % 128 == 0 && C <= CP);
   cudaStream_t st = as_stream(stream);
   const int64_t per_cloud = (int64_t)NP * (c1 + c2 + c3) * sizeof(float);
-  const int chunk = (int)std::min<int64_t>(R, workspace_bytes / per_cloud);
+  // TF32 tier: the tensor core truncates its operands to 10 mantissa bits; feeding it values already ROUNDED to TF32
+  // halves the error and removes its bias.  Activations are rounded by their producers (relu flag bit 1), the two
+  // weight matrices into copies at the end of the workspace.
+  const int64_t wbytes = tf32 ? align_up((int64_t)(c2 * c1 + c3 * c2) * 4, 256) : 0;
+  PCRL_CHECK_ARG(workspace_bytes > wbytes);
+  const int chunk = (int)std::min<int64_t>(R, (workspace_bytes - wbytes) / per_cloud);
   PCRL_CHECK_ARG(chunk >= 1 || R == 0);
+  const int rnd = tf32 ? 2 : 0;
+  if (tf32 && R > 0) {
+    float* w1r = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + workspace_bytes - wbytes);
+    float* w2r = w1r + c2 * c1;
+    round_tf32_kernel<<<(unsigned)cdiv(c2 * c1, 256), 256, 0, st>>>(w1, w1r, c2 * c1);
+    round_tf32_kernel<<<(unsigned)cdiv(c3 * c2, 256), 256, 0, st>>>(w2, w2r, c3 * c2);
+    PCRL_CHECK_LAUNCH();
+    w1 = w1r;
+    w2 = w2r;
+  }
   for (int r0 = 0; r0 < R; r0 += chunk) {
     const int rows = std::min(chunk, R - r0);
     const int P = rows * NP;
@@ -357,12 +446,33 @@ static int pointnet_fwd_chain(const float* xf, int R, int N, int NP, int CP, int
     const float* x = xf + (int64_t)r0 * NP * CP;
     int rc;
     // h0 = relu(x W0^T + b0)                     (conv0 + ReLU; no norm: ignore_first_ln)
-    if ((rc = gemm_nt(x, CP, w0, C, b0, 1, h0, c1, P, C, c1, nullptr, st))) return rc;
+    if ((rc = gemm_nt(x, CP, w0, C, b0, 1 | rnd, h0, c1, P, C, c1, nullptr, st))) return rc;
     // h1 = relu(LN(h0 W1^T))
     if ((rc = gemm_nt(h0, c1, w1, c1, nullptr, 0, h1, c2, P, c1, c2, nullptr, st, tf32))) return rc;
-    if ((rc = launch_ln_rows(h1, c2, g1, be1, h1, c2, nullptr, nullptr, P, c2, ln_eps, 1, nullptr, st))) return rc;
+    if ((rc = launch_ln_rows(h1, c2, g1, be1, h1, c2, nullptr, nullptr, P, c2, ln_eps, 1 | rnd, nullptr, st))) return rc;
     // h2 = relu(LN(h1 W2^T))
     if ((rc = gemm_nt(h1, c2, w2, c2, nullptr, 0, h2, c3, P, c2, c3, nullptr, st, tf32))) return rc;
+    if (c3 % 32 == 0 && c3 <= 1024 && (int64_t)rows * c3 * 8 <= (int64_t)P * c1 * 4) {
+      // fused LayerNorm + ReLU + max-pool; the packed maxima live in the h0 region (dead since layer 1's GEMM)
+      auto* keys = reinterpret_cast<unsigned long long*>(h0);
+      PCRL_CHECK_CUDA(cudaMemsetAsync(keys, 0, (size_t)rows * c3 * 8, st));
+      const int slices = (int)std::max<int64_t>(1, std::min<int64_t>(cdiv(N, 8), cdiv(2 * sm_count(), rows)));
+      dim3 grid((unsigned)slices, (unsigned)rows);
+      switch (c3 / 32) {
+        case 4: ln_relu_maxpool_kernel<4><<<grid, 256, 0, st>>>(h2, N, NP, c3, g2, be2, ln_eps, keys); break;
+        case 8: ln_relu_maxpool_kernel<8><<<grid, 256, 0, st>>>(h2, N, NP, c3, g2, be2, ln_eps, keys); break;
+        case 16: ln_relu_maxpool_kernel<16><<<grid, 256, 0, st>>>(h2, N, NP, c3, g2, be2, ln_eps, keys); break;
+        case 32: ln_relu_maxpool_kernel<32><<<grid, 256, 0, st>>>(h2, N, NP, c3, g2, be2, ln_eps, keys); break;
+        default: keys = nullptr;
+      }
+      if (keys) {
+        PCRL_CHECK_LAUNCH();
+        finalize_keys_kernel<<<(unsigned)cdiv((int64_t)rows * c3, 256), 256, 0, st>>>(
+            keys, (int64_t)rows * c3, pooled + (int64_t)r0 * c3, argmax ? argmax + (int64_t)r0 * c3 : nullptr);
+        PCRL_CHECK_LAUNCH();
+        continue;
+      }
+    }
     if ((rc = launch_ln_rows(h2, c3, g2, be2, h2, c3, nullptr, nullptr, P, c3, ln_eps, 1, nullptr, st))) return rc;
     dim3 grid((unsigned)cdiv(c3, 256), (unsigned)rows);
     maxpool_points_kernel<<<grid, 256, 0, st>>>(h2, rows, N, NP, c3, pooled + (int64_t)r0 * c3,

@@ -30,7 +30,8 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
       float xh = (xr[c] - mean) * rstd;
       if (xhat) xhat[(int64_t)i * D + c] = xh;
       float o = fmaf(xh, g[c], b[c]);
-      if (relu) o = fmaxf(o, 0.f);
+      if (relu & 1) o = fmaxf(o, 0.f);
+      if (relu & 2) o = round_tf32(o);  // the row feeds a TF32 GEMM: round instead of letting the tensor core truncate
       yr[c] = o;
     }
   }

@@ -122,7 +122,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
       if (g.accumulate) {
         atomicAdd(c, v);
       } else {
-        if (g.relu) v = fmaxf(v, 0.f);
+        if (g.relu & 1) v = fmaxf(v, 0.f);
+        if (g.relu & 2) v = round_tf32(v);
         if (g.mask && !(g.mask[(int64_t)gi * g.ldmask + gj] > 0.f)) v = 0.f;
         *c = v;
       }

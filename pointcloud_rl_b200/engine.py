@@ -261,7 +261,8 @@ class UpdateEngine:
         w["dx0"] = torch.zeros(R, D + S + A, **f32)
         w["dx1"] = torch.zeros(R, D + S + A, **f32)
         chunk = max(1, min(R, fwd_chunk_clouds))
-        self.fwd_ws_bytes = int(self.L.pointnet_fwd_f32_workspace(chunk, NP, c1, c2, c3))
+        ws_query = self.L.pointnet_fwd_tf32_workspace if self.precision == "tf32" else self.L.pointnet_fwd_f32_workspace
+        self.fwd_ws_bytes = int(ws_query(chunk, NP, c1, c2, c3))
         self.bwd_ws_bytes = int(self.L.pointnet_bwd_workspace(R, NP, c1, c2, c3, CP))
         w["scratch"] = torch.zeros(max(self.fwd_ws_bytes, self.bwd_ws_bytes), dtype=torch.uint8, device=dev)
         if not bf16:

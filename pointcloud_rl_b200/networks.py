@@ -184,7 +184,8 @@ class KernelRunner:
                 ws["keys"] = torch.zeros(B * c3, dtype=torch.int64, device=device)
             else:
                 chunk = max(1, min(B, 32 if self.precision == "tf32" else 64))
-                ws["fwd_bytes"] = int(L.pointnet_fwd_f32_workspace(chunk, spec.NP, c1, c2, c3))
+                query = L.pointnet_fwd_tf32_workspace if self.precision == "tf32" else L.pointnet_fwd_f32_workspace
+                ws["fwd_bytes"] = int(query(chunk, spec.NP, c1, c2, c3))
                 ws["scratch"] = torch.zeros(ws["fwd_bytes"], dtype=torch.uint8, device=device)
             self._ws[key] = ws
         return ws
