@@ -48,7 +48,7 @@ WORKLOADS = {
     # BASELINE.json configs[4]: wide PointNet (pointnet.py:81 default mlp_spec) SAC update, N=16384, B=512
     "sac_wide": dict(algo="sac", cfg="mfrl/sac/dm_control/pn.py", B=512, N=16384, n_seg=0, n_pos=0, S=0, A=6,
                      widths=(64, 128, 1024), D=256, hidden=(1024, 1024), num_aug=1, aug=None, aug_lo=0.0, aug_hi=0.0,
-                     gamma=0.99, zero_out_logstd=False,
+                     gamma=0.99, zero_out_logstd=False, cpu_sample_B=2,  # the reference's activations alone are 34 GB at B=512
                      overrides={"actor_cfg.nn_cfg.visual_nn_cfg.mlp_spec": [64, 128, 1024],
                                 "actor_cfg.nn_cfg.visual_nn_cfg.out_channels": 256,
                                 "actor_cfg.nn_cfg.mlp_cfg.mlp_spec": ["256", 1024, 1024, "action_shape * 2"],
@@ -257,10 +257,12 @@ def reference_arm(args, w, rank, world):
     cores = os.cpu_count() or 1
     # one probe update at 1/8 of the batch sizes the slice (cost is linear in B to within a few percent)
     B = w["B"]
-    t_probe, kind, _ = reference_seconds_per_update(args.workload, w, "cpu", 1, 1, threads=cores, batch_size=max(8, B // 8))
-    t_full_est = t_probe * B / max(8, B // 8)
-    B_s = B
-    while B_s > 8 and (args.steps + args.warmup) * t_full_est * B_s / B > 270.0:
+    B_cap = int(w.get("cpu_sample_B", B))
+    B_probe = min(B_cap, max(8, B // 8))
+    t_probe, kind, _ = reference_seconds_per_update(args.workload, w, "cpu", 1, 1, threads=cores, batch_size=B_probe)
+    t_full_est = t_probe * B / B_probe
+    B_s = B_cap
+    while B_s > min(8, B_cap) and (args.steps + args.warmup) * t_full_est * B_s / B > 270.0:
         B_s //= 2
     t, kind, ret = reference_seconds_per_update(args.workload, w, "cpu", args.steps, args.warmup, threads=cores, batch_size=B_s)
     t_full = t * (B / B_s)
@@ -516,14 +518,20 @@ def native_arm(args, w, rank, world, local_rank):
     pts1 = encoded_points_per_update(w)
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
+        B_s = int(w.get("cpu_sample_B", w["B"]))
         try:
-            t, kind, _ = reference_seconds_per_update(args.workload, w, "cpu", 2, 1, threads=cores)
+            t, kind, _ = reference_seconds_per_update(args.workload, w, "cpu", 2, 1, threads=cores, batch_size=B_s)
+            t *= w["B"] / B_s
             what = "the unmodified reference (oracle/_ref)" if kind == "reference" else "oracle port"
+            size = f"the full B={w['B']} batch" if B_s == w["B"] else f"a B={B_s} slice of the batch, scaled x{w['B'] // B_s}"
             cpu = {"value": pts1 / t, "unit": "points/s", "cores": cores, "kind": kind, "steps_per_s": 1.0 / t,
-                   "sample": f"{what}, 1 warm-up + 2 timed updates of the full B={w['B']} batch"}
+                   "sample": f"{what}, 1 warm-up + 2 timed updates of {size}"}
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": "points/s", "cores": cores, "kind": "unavailable", "sample": repr(e)[:200]}
         try:
+            if B_s != w["B"]:
+                raise RuntimeError("the reference's dense autograd does not fit this configuration on one GPU "
+                                   "(34 GB per saved activation at B=512, N=16384, c3=1024)")
             t, kind, _ = reference_seconds_per_update(args.workload, w, device, 10, 3)
             cuda_ref = {"value": pts1 / t, "unit": "points/s", "ms_per_step": t * 1e3, "kind": kind,
                         "what": "the unmodified reference moved to this GPU with .to('cuda'), torch eager fp32 "

@@ -6,6 +6,7 @@
 
 namespace pcrl {
 namespace tc {
+bool recompute_supported(int c1, int c2, int c3);
 int recompute_active_tc(const void* xh, const void* wpack, const int32_t* src, const int* count_dev, int capacity,
                         int c1, int c2, int c3, float ln_eps, void* xha_scratch, float* h0, float* xhat1, float* rstd1,
                         float* h1, float* xhat2, float* rstd2, const float* m1, const float* m2, cudaStream_t st);
@@ -539,7 +540,9 @@ int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, cons
   int rc;
 
   // 1. which points carry gradient; compact them and gather their staged rows
-  const bool fast = xh && wpack;
+  // the fused recompute (first-generation tcgen05 kernel in dump mode) covers widths up to (256, 256, 256); wider
+  // PointNets recompute their compacted rows on the GEMM chain below (TF32 tcgen05 GEMMs when tf32 != 0)
+  const bool fast = xh && wpack && tc::recompute_supported(c1, c2, c3);
   mark_count_kernel<<<R, 256, 0, st>>>(pooled, argmax, dpooled, NP, c3, w.flag, w.counts);
   PCRL_CHECK_LAUNCH();
   // (fast mode: w.d0 doubles as the gathered bf16 tile scratch, it is only written at the very end of the backward)

@@ -700,6 +700,8 @@ static bool shapes_ok(int c1, int c2, int c3) {
          make_layout(c1, c2, c3).total <= 227 * 1024;
 }
 
+bool recompute_supported(int c1, int c2, int c3) { return shapes_ok(c1, c2, c3); }
+
 // Recompute of the compacted active points on the fused tensor-core kernel (called by pcrl_pointnet_bwd in fast mode):
 // gathers their bf16 tile rows, runs the three layers and writes h0 / xhat1 / rstd1 / h1 / xhat2 / rstd2 (fp32).
 int recompute_active_tc(const void* xh, const void* wpack, const int32_t* src, const int* count_dev, int capacity,
@@ -754,7 +756,9 @@ int pcrl_debug_set_fwd_version(int v) {
 int pcrl_debug_set_fwd2_flags(int flags) { return tc2::set_debug_flags(flags); }
 int pcrl_debug_get_trace2(long long* out_host) { return tc2::get_trace(out_host); }
 // first-generation image (also read by the backward's recompute), then the second-generation image, 128-byte aligned
-static int64_t wpack1_bytes(int c1, int c2, int c3) { return align_up((int64_t)tc::make_wpack(c1, c2, c3).total, 128); }
+static int64_t wpack1_bytes(int c1, int c2, int c3) {
+  return tc::shapes_ok(c1, c2, c3) ? align_up((int64_t)tc::make_wpack(c1, c2, c3).total, 128) : 0;
+}
 
 int64_t pcrl_pointnet_wpack_bytes(int c1, int c2, int c3) { return wpack1_bytes(c1, c2, c3) + tc2::wpack_bytes(c1, c2, c3); }
 
@@ -762,15 +766,16 @@ int pcrl_pointnet_pack_weights_part(const float* w0, const float* b0, const floa
                                     const float* w2, const float* g2, const float* be2, int C, int c1, int c2, int c3,
                                     int rgb_u8, int which, void* wpack, void* stream) {
   PCRL_CHECK_ARG(w0 && b0 && w1 && g1 && be1 && w2 && g2 && be2 && wpack);
-  if (C + 4 > 16 || !tc::shapes_ok(c1, c2, c3)) {
-    set_error("pcrl_pointnet_pack_weights: shape unsupported by the tcgen05 path (C=%d <= 12, widths (%d,%d,%d) multiples of 64/64/128 "
-              "up to 256 with max(c1,c2) + 1.5*c3 <= 512 TMEM columns); use the fp32 path", C, c1, c2, c3);
+  const bool v1 = tc::shapes_ok(c1, c2, c3), v2 = tc2::shapes_ok(c1, c2, c3);
+  if (C + 4 > 16 || !(v1 || v2)) {
+    set_error("pcrl_pointnet_pack_weights: shape unsupported by the tcgen05 path (C=%d <= 12; widths (%d,%d,%d): c1 in {64,128}, "
+              "c2 = 128, c3 = 128 or a multiple of 256 up to 2048 -- or c1, c2 multiples of 64 and c3 of 128 up to 256 with "
+              "max(c1,c2) + 1.5*c3 <= 512 TMEM columns); use the tf32 / fp32 path", C, c1, c2, c3);
     return PCRL_EUNSUPPORTED;
   }
-  const bool v2 = tc2::shapes_ok(c1, c2, c3);
-  // the first-generation image feeds the backward's recompute, and the forward too where the second generation
-  // does not cover the shape
-  if ((which & PCRL_WPACK_BWD) || ((which & PCRL_WPACK_FWD) && !v2)) {
+  // the first-generation image feeds the backward's recompute (shapes it covers; wider PointNets recompute on the TF32
+  // GEMMs instead), and the forward too where the second generation does not cover the shape
+  if (v1 && ((which & PCRL_WPACK_BWD) || ((which & PCRL_WPACK_FWD) && !v2))) {
     const int n = c1 * 16 + c2 * c1 + c3 * c2 + 2 * c2 + 2 * c3 + c3;
     tc::pack_weights_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(w0, b0, w1, g1, be1, w2, g2, be2, C,
                                                                                      c1, c2, c3, rgb_u8, (char*)wpack);
@@ -798,7 +803,7 @@ int pcrl_pointnet_fwd_bf16_strided(const void* xh, int R, int src_cloud_stride, 
                                    int c2, int c3, float ln_eps, uint64_t* pool_keys, float* pooled, int32_t* argmax,
                                    void* stream) {
   PCRL_CHECK_ARG(xh && wpack && pool_keys && pooled && R >= 0 && N > 0 && NP >= N && NP % 128 == 0 && src_cloud_stride >= 1);
-  if (!tc::shapes_ok(c1, c2, c3)) {
+  if (!tc::shapes_ok(c1, c2, c3) && !tc2::shapes_ok(c1, c2, c3)) {
     set_error("pcrl_pointnet_fwd_bf16: widths (%d,%d,%d) unsupported (multiples of 64/64/128 up to 256, max(c1,c2) + 1.5*c3 <= 512, smem budget)", c1,
               c2, c3);
     return PCRL_EUNSUPPORTED;

@@ -159,11 +159,19 @@ __device__ __forceinline__ void tmem_chunks1(uint32_t taddr, bool skip_loads, F&
 template <int C1, int C2, int NBLK, bool ARGMAX>
 __global__ void __launch_bounds__(kThreads, 1)
 pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wpack, int n_tiles, int tiles_per_cloud,
-                        int src_cloud_stride, float ln_eps, float key_bias, unsigned long long* __restrict__ pool_keys) {
-  constexpr int C3 = NBLK * 128;
+                        int src_cloud_stride, float ln_eps, float key_bias, unsigned long long* __restrict__ pool_keys,
+                        int c3_total, int ctas_per_group) {
+  // Channel groups (wide last layers, c3_total > NBLK * 128): the layer-2 weights no longer fit in shared memory, so
+  // the CTAs split into c3_total / (NBLK * 128) groups; a group keeps ITS NBLK blocks of W2c' resident, walks all the
+  // tiles (recomputing layers 0 / 1 and the Gram product, whose variance covers all c3_total channels) and pools its
+  // own channels.  Config 2 (c3 = 256) is one group.
+  constexpr int C3G = NBLK * 128;                       // channels this CTA pools
+  const int group = (int)blockIdx.x / ctas_per_group;   // which NBLK-block slice of W2c'
+  const int cta_in_group = (int)blockIdx.x % ctas_per_group;
   extern __shared__ __align__(128) unsigned char smem[];
-  const Smem2 L = make_smem2(C1, C2, C3);
-  const Wpack2 W = make_wpack2(C1, C2, C3);
+  const Smem2 L = make_smem2(C1, C2, C3G);
+  const Wpack2 W = make_wpack2(C1, C2, C3G);            // shared-memory image (one group's W2c' slice)
+  const Wpack2 WG = make_wpack2(C1, C2, c3_total);      // global image (all of W2c')
   const uint32_t sbase = smem_u32(smem);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // provably warp-uniform
   constexpr uint32_t kActBytes = 128 * (C1 > C2 ? C1 : C2) * 2;
@@ -225,9 +233,9 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
 #endif
 
   // every CTA takes a contiguous range of tiles (consecutive tiles belong to the same cloud)
-  const int t_q = n_tiles / (int)gridDim.x, t_r = n_tiles % (int)gridDim.x;
-  const int n_local = t_q + ((int)blockIdx.x < t_r ? 1 : 0);
-  const int64_t tile0 = (int64_t)blockIdx.x * t_q + min((int)blockIdx.x, t_r);
+  const int t_q = n_tiles / ctas_per_group, t_r = n_tiles % ctas_per_group;
+  const int n_local = t_q + (cta_in_group < t_r ? 1 : 0);
+  const int64_t tile0 = (int64_t)cta_in_group * t_q + min(cta_in_group, t_r);
   const uint32_t s_w0 = sbase + L.img + W.w0, s_w1 = sbase + L.img + W.w1, s_gc = sbase + L.img + W.gc,
                  s_w2 = sbase + L.img + W.w2;
 
@@ -235,8 +243,14 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       mbar_expect_tx(BAR(WB), W.img_bytes);
-      for (uint32_t off = 0; off < W.img_bytes; off += 32768u)
-        bulk_g2s(sbase + L.img + off, wpack + off, min(W.img_bytes - off, 32768u), BAR(WB));
+      // [W0' | W1c | Gc] is contiguous in both images; then this group's slice of W2c'; then g1 | be1
+      for (uint32_t off = 0; off < W.w2; off += 32768u)
+        bulk_g2s(sbase + L.img + off, wpack + off, min(W.w2 - off, 32768u), BAR(WB));
+      const uint32_t w2_bytes = W.prm1 - W.w2;
+      for (uint32_t off = 0; off < w2_bytes; off += 32768u)
+        bulk_g2s(sbase + L.img + W.w2 + off, wpack + WG.w2 + (uint32_t)group * w2_bytes + off, min(w2_bytes - off, 32768u),
+                 BAR(WB));
+      bulk_g2s(sbase + L.img + W.prm1, wpack + WG.prm1, W.img_bytes - W.prm1, BAR(WB));
       for (int i = 0; i < n_local; ++i) {
         const int st = i % kStages;
         if (i >= kStages) mbar_wait_relaxed(BAR(XE + st), ((i / kStages) - 1) & 1, 64);
@@ -338,6 +352,7 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
     unsigned char* dst0 = abuf + (row >> 3) * (uint32_t)(C1 * 16) + (row & 7) * 16;
     unsigned char* dst1 = abuf + (row >> 3) * (uint32_t)(C2 * 16) + (row & 7) * 16;
     float* rbuf = reinterpret_cast<float*>(smem + L.rbuf);
+    const float inv_c3 = 1.0f / (float)c3_total;
     const bool no_ld = dbg & 8;
     mbar_wait(BAR(WB), 0);  // LN parameters landed
     Tracer2 tr{3 + s, 0, (dbg & 256) && blockIdx.x == 0 && lane == 0 && q == 0};
@@ -436,7 +451,7 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
         unpk2(d01, a, b);
         unpk2(d23, c, d);
         const float ss = (__uint_as_float(a) + __uint_as_float(b)) + (__uint_as_float(c) + __uint_as_float(d));
-        rbuf[(j & 3) * 128 + row] = rsqrtf(fmaxf(ss, 0.f) * (1.0f / (float)C3) + ln_eps);
+        rbuf[(j & 3) * 128 + row] = rsqrtf(fmaxf(ss, 0.f) * inv_c3 + ln_eps);
       }
       tc_fence_before();
       mbar_arrive(BAR(EU + s));
@@ -465,7 +480,7 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
         } else {
           key = (unsigned long long)(__float_as_uint(m[b] + key_bias) & 0xffffff80u) << 32;  // same bits as the argmax variant
         }
-        atomicMax(pool_keys + (int64_t)cloud * C3 + b * 128 + q * 32 + lane, key);
+        atomicMax(pool_keys + (int64_t)cloud * c3_total + group * C3G + b * 128 + q * 32 + lane, key);
         m[b] = -3.0e38f;
         run[b] = 0ull;
       }
@@ -649,7 +664,9 @@ gram_kernel(const float* __restrict__ w2, const float* __restrict__ m2, int c2, 
 }
 
 bool shapes_ok(int c1, int c2, int c3) {
-  return (c1 == 64 || c1 == 128) && c2 == 128 && (c3 == 128 || c3 == 256) && make_smem2(c1, c2, c3).total <= 227 * 1024;
+  // c3 a multiple of 256 up to 2048: c3 / 256 channel groups of CTAs (the packer's column-mean kernel covers c3 <= 2048)
+  return (c1 == 64 || c1 == 128) && c2 == 128 && (c3 == 128 || (c3 % 256 == 0 && c3 <= 2048)) &&
+         make_smem2(c1, c2, std::min(c3, 256)).total <= 227 * 1024;
 }
 
 int64_t wpack_bytes(int c1, int c2, int c3) { return shapes_ok(c1, c2, c3) ? (int64_t)make_wpack2(c1, c2, c3).total : 0; }
@@ -671,19 +688,21 @@ int pack(const float* w0, const float* b0, const float* w1, const float* g1, con
 
 template <int C1, int C2, int NBLK>
 static int launch(const void* xh, const void* wpack2, int n_tiles, int tiles_per_cloud, int src_cloud_stride, float ln_eps,
-                  float key_bias, unsigned long long* keys, bool want_argmax, cudaStream_t st) {
+                  float key_bias, unsigned long long* keys, bool want_argmax, int c3_total, cudaStream_t st) {
   const Smem2 L = make_smem2(C1, C2, NBLK * 128);
-  const int grid = std::min(sm_count(), n_tiles);
+  const int groups = c3_total / (NBLK * 128);
+  const int ctas_per_group = std::max(1, std::min(sm_count() / groups, n_tiles));
+  const int grid = groups * ctas_per_group;
   if (want_argmax) {
     auto* kern = pointnet_fwd_tc2_kernel<C1, C2, NBLK, true>;
     PCRL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     kern<<<grid, kThreads, L.total, st>>>((const char*)xh, (const char*)wpack2, n_tiles, tiles_per_cloud, src_cloud_stride,
-                                          ln_eps, key_bias, keys);
+                                          ln_eps, key_bias, keys, c3_total, ctas_per_group);
   } else {
     auto* kern = pointnet_fwd_tc2_kernel<C1, C2, NBLK, false>;
     PCRL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     kern<<<grid, kThreads, L.total, st>>>((const char*)xh, (const char*)wpack2, n_tiles, tiles_per_cloud, src_cloud_stride,
-                                          ln_eps, key_bias, keys);
+                                          ln_eps, key_bias, keys, c3_total, ctas_per_group);
   }
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
@@ -698,10 +717,11 @@ int forward(const void* xh, int R, int src_cloud_stride, int NP, const void* wpa
   auto* keys = reinterpret_cast<unsigned long long*>(pool_keys);
   int rc = PCRL_EUNSUPPORTED;
   const bool am = argmax != nullptr;
-  if (c1 == 128 && c3 == 256) rc = launch<128, 128, 2>(xh, wpack2, n_tiles, tiles_per_cloud, src_cloud_stride, ln_eps, key_bias, keys, am, st);
-  else if (c1 == 64 && c3 == 256) rc = launch<64, 128, 2>(xh, wpack2, n_tiles, tiles_per_cloud, src_cloud_stride, ln_eps, key_bias, keys, am, st);
-  else if (c1 == 128 && c3 == 128) rc = launch<128, 128, 1>(xh, wpack2, n_tiles, tiles_per_cloud, src_cloud_stride, ln_eps, key_bias, keys, am, st);
-  else if (c1 == 64 && c3 == 128) rc = launch<64, 128, 1>(xh, wpack2, n_tiles, tiles_per_cloud, src_cloud_stride, ln_eps, key_bias, keys, am, st);
+  // c3 = 128: one block; otherwise groups of two 128-channel blocks (c3 = 256: one group; 1024: four groups of CTAs)
+  if (c1 == 128 && c3 % 256 == 0) rc = launch<128, 128, 2>(xh, wpack2, n_tiles, tiles_per_cloud, src_cloud_stride, ln_eps, key_bias, keys, am, c3, st);
+  else if (c1 == 64 && c3 % 256 == 0) rc = launch<64, 128, 2>(xh, wpack2, n_tiles, tiles_per_cloud, src_cloud_stride, ln_eps, key_bias, keys, am, c3, st);
+  else if (c1 == 128 && c3 == 128) rc = launch<128, 128, 1>(xh, wpack2, n_tiles, tiles_per_cloud, src_cloud_stride, ln_eps, key_bias, keys, am, c3, st);
+  else if (c1 == 64 && c3 == 128) rc = launch<64, 128, 1>(xh, wpack2, n_tiles, tiles_per_cloud, src_cloud_stride, ln_eps, key_bias, keys, am, c3, st);
   if (rc != PCRL_OK) return rc;
   const int64_t n = (int64_t)R * c3;
   const Wpack2 W = make_wpack2(c1, c2, c3);

@@ -80,13 +80,53 @@ def test_terminal_transitions_and_reward_scale():
     _compare_update("sac", 6, 150, 3, 7, 0, (64, 128, 256), 24, batch_mod=dones, hp_extra=dict(ignore_dones=True))
 
 
-def test_wide_pointnet_runs_on_the_fp32_path():
-    """BASELINE config 5 shape class (64-128-1024 per-point MLP): supported by the exact-fp32 kernels."""
+def test_wide_pointnet_on_every_tier():
+    """BASELINE config 5 shape class (pointnet.py:81 default 64-128-1024 per-point MLP): exact fp32 kernels, the TF32
+    GEMM chain, and the fused tcgen05 forward (the 1024 output channels split over four groups of CTAs, each keeping
+    its 256 x 128 slice of W2 resident; the backward recomputes on the TF32 GEMMs)."""
     _compare_update("sac", 2, 300, 3, 0, 0, (64, 128, 1024), 64)
-    from pointcloud_rl_b200._lib import PcrlError
+    _compare_update("sac", 3, 700, 3, 0, 0, (64, 128, 1024), 64, precision="tf32", tol=5e-3, updates=1)
+    _compare_update("sac", 3, 700, 3, 0, 0, (64, 128, 1024), 64, precision="bf16", tol=2e-2, updates=1)
 
-    with pytest.raises(PcrlError, match="unsupported"):
-        _compare_update("sac", 2, 300, 3, 0, 0, (64, 128, 1024), 64, precision="bf16")
+
+def test_wide_pointnet_forward_bf16_matches_oracle():
+    """The fused forward at c3 = 1024 against the fp32 oracle: pooled features within the bf16 tolerance, argmax a
+    near-tie of the true maximum, duplicated tail points never selected."""
+    from pointcloud_rl_b200._lib import lib, stream_ptr
+
+    L = lib()
+    rs = np.random.RandomState(2)
+    R, N, C = 3, 1500, 6
+    obs = O.synthetic_obs(rs, R, N, duplicate_tail=True)
+    t = {k: torch.from_numpy(v) for k, v in obs.items()}
+    p = O.init_params(4, C, (64, 128, 1024), 32, 0, 3, hidden=16)
+    gen = torch.Generator().manual_seed(3)
+    p["pn.g2"] = p["pn.g2"] * torch.where(torch.rand(1024, generator=gen) < 0.3, -1.0, 1.0) * (0.5 + torch.rand(1024, generator=gen))
+    p["pn.be2"] = 0.2 * torch.randn(1024, generator=gen)
+    x = O.preprocess(t)
+    _, ref_pooled, _ = O.pointnet_forward(p, x, return_pool=True)
+    NP = (N + 127) // 128 * 128
+    xf = torch.zeros(R, NP, 8, device="cuda")
+    xh = torch.zeros(R * NP * 16, dtype=torch.bfloat16, device="cuda")
+    st = stream_ptr()
+    L.stage_points(t["xyz"].cuda(), t["rgb"].cuda(), 1, None, 0, None, 0, R, N, 1, 0, 0.0, 0.0, None, 0, None, 0, xf, xh, 8, st)
+    d = {k: v.cuda().contiguous() for k, v in p.items()}
+    wpack = torch.zeros(int(L.pointnet_wpack_bytes(64, 128, 1024)), dtype=torch.uint8, device="cuda")
+    L.pointnet_pack_weights(d["pn.w0"], d["pn.b0"], d["pn.w1"], d["pn.g1"], d["pn.be1"], d["pn.w2"], d["pn.g2"], d["pn.be2"],
+                            C, 64, 128, 1024, 1, wpack, st)
+    keys = torch.zeros(R * 1024, dtype=torch.int64, device="cuda")
+    pooled = torch.empty(R, 1024, device="cuda")
+    argmax = torch.empty(R, 1024, dtype=torch.int32, device="cuda")
+    L.pointnet_fwd_bf16(xh, R, N, NP, wpack, 64, 128, 1024, 1e-6, keys, pooled, argmax, st)
+    torch.cuda.synchronize()
+    err = float((pooled.cpu() - ref_pooled).norm() / ref_pooled.norm())
+    assert err < 2e-2, err
+    idx = argmax.cpu().long()
+    assert int(idx.min()) >= 0 and int(idx.max()) < N - N // 4
+    h = O.pointnet_point_features(p, x)
+    v_ours = torch.gather(h, 2, idx[..., None])[..., 0]
+    assert float((ref_pooled - v_ours).max()) < 0.05 * float(ref_pooled.max())
+    assert int(keys.abs().max()) == 0
 
 
 def test_fast_mode_edge_sizes():
