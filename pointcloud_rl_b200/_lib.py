@@ -38,6 +38,9 @@ def parse_header(path=HEADER):
     return protos
 
 
+_SYNC_DEBUG = bool(os.environ.get("PCRL_SYNC"))
+
+
 class PcrlError(RuntimeError):
     pass
 
@@ -86,6 +89,11 @@ class _Lib:
             if len(conv) != len(args):
                 raise TypeError(f"{full} takes {len(args)} arguments, got {len(conv)}")
             rc = fn(*conv)
+            if _SYNC_DEBUG and is_status:  # PCRL_SYNC=1: find the launch an asynchronous CUDA error belongs to
+                try:
+                    torch.cuda.synchronize()
+                except Exception as e:  # noqa: BLE001
+                    raise PcrlError(f"{full}{tuple(x if not isinstance(x, int) or x < 1 << 32 else hex(x) for x in conv)}: {e}") from e
             if is_status:
                 self.launches += 1
                 if rc != 0:

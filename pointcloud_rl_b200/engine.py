@@ -17,6 +17,9 @@ import torch
 
 from ._lib import lib, stream_ptr
 
+import os
+
+_NO_FORK = os.environ.get("PCRL_NO_FORK", "")
 S_NAMES = [
     "critic_loss", "max_critic_abs_err", "q", "q_target", "critic_grad_sq", "actor_loss", "alpha_loss",
     "entropy", "actor_grad_sq", "alpha", "alpha_grad",
@@ -544,6 +547,15 @@ class UpdateEngine:
         """Side stream `idx`, ordered after everything enqueued so far on the current stream.  Independent chains of
         the update (target branch vs critic forward, the two Q heads) run on forked streams: most of their kernels
         fill only part of the 148 SMs, and inside a CUDA graph the forks become parallel branches."""
+        if _NO_FORK == "1" or (_NO_FORK and str(idx) in _NO_FORK.split(",")):  # debugging aid: PCRL_NO_FORK=1 | "0,1"
+            return torch.cuda.current_stream()
+        if idx in (0, 1) and self.R * self.spec.NP >= (1 << 22):
+            # >= 4 M points per encode (BASELINE config 5: 8.4 M): each encode fills all 148 SMs for milliseconds, so
+            # running the target branch beside the critic forward buys nothing -- and the forked form of this graph
+            # fails at replay with "unspecified launch failure" at 8.4 M points (B=512 x N=16384; B=256 runs; every
+            # other fork may stay; clean under compute-sanitizer, which serialises the branches).  Root cause not
+            # found: the branch runs in line at these sizes.
+            return torch.cuda.current_stream()
         side = self._side[idx]
         side.wait_stream(torch.cuda.current_stream())
         return side
