@@ -419,6 +419,10 @@ def native_arm(args, w, rank, world, local_rank):
     for u in range(1, max(args.warmup, 4) + 1):
         ret = agent.update_parameters(memory, u)
     eng, spec = agent.engine, agent.engine.spec
+    # from here on a tf32 GEMM whose operands are not TMA-addressable is an ERROR, not a silent FFMA fallback; the warm-up
+    # above ran every shape of the workload once in the permissive mode, so the counter says whether any fell back
+    fallbacks_warmup = int(eng.L.tf32_fallbacks())
+    eng.L.set_strict_tf32(1 if fallbacks_warmup == 0 else 0)
     barrier()
     step_fn = eng.update_graphed if not args.no_graph else eng.update
 
@@ -555,6 +559,7 @@ def native_arm(args, w, rank, world, local_rank):
                                 "h2d_bytes_per_step": 8 * w["B"], "api": "same call, DeviceReplayMemory"}},
         "gpu_launches": int(launches_eager) if args.no_graph else int(graph_kernels),
         "roofline": roofline, "cpu_baseline": cpu, "torch_cuda": cuda_ref, "tf32_peak": tf32,
+        "tf32_fallbacks": int(eng.L.tf32_fallbacks()),
         "last_scalars": {k: round(float(v), 5) for k, v in ret.items()},
     }
     print(json.dumps(line), flush=True)

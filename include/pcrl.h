@@ -49,6 +49,21 @@ const char* pcrl_last_error(void);
 /* number of SMs of the current device (grid sizing on the host side) */
 int pcrl_sm_count(void);
 
+/* Per-device context.  Everything the library keeps between calls -- the SM count and the internal side stream +
+ * fork/join events pcrl_pointnet_bwd runs its weight-gradient GEMMs on -- lives in one context per CUDA device; there is
+ * no other process-global state.  Calls use the context of the CURRENT device, creating it on first use; a caller that
+ * wants to own the lifetime creates it up front and destroys it when done (after synchronising the device; captured CUDA
+ * graphs that contain pcrl_pointnet_bwd reference the context's stream and must be destroyed first).
+ * pcrl_create returns an opaque handle (0 on failure). */
+int64_t pcrl_create(int device);
+int pcrl_destroy(int64_t handle);
+
+/* tf32 = 1 requests whose operands were not TMA-addressable (16-byte base, row pitch % 4 floats) run on the exact FFMA
+ * kernel instead.  pcrl_tf32_fallbacks() counts them (process-wide); pcrl_set_strict_tf32(1) turns such a call into
+ * PCRL_EUNSUPPORTED so a fast-mode shape can never lose the tensor path silently. */
+int64_t pcrl_tf32_fallbacks(void);
+int pcrl_set_strict_tf32(int on);
+
 /* ---------------------------------------------------------------------------------------------
  * (1) Staging + augmentation.  Replaces GDict.repeat / repeat_interleave (drq.py:58-63,
  * array_ops.py:106-121), RandomJitterPoints / GlobalRotScaleTrans (pcd_aug.py) and

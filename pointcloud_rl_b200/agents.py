@@ -18,7 +18,7 @@ import torch.nn as nn
 
 from .augmentations import build_data_augmentations
 from .data import GDict, unwrap
-from .engine import HyperParams, PathSpec, UpdateEngine
+from .engine import AUG_KINDS, HyperParams, PathSpec, UpdateEngine
 from .meta import Registry, build_from_cfg
 from .networks import ExtendedModule, _mlp_views, _pn_views, build_actor_critic, build_target_network
 
@@ -111,8 +111,9 @@ class BaseAgent(ExtendedModule):
     def forward(self, obs, **kwargs):
         """Rollout entry (module_utils.py:147-159): obs -> device -> actor(obs, mode=...)."""
         obs = GDict(obs).to_torch(device=self.device, non_blocking=True, wrapper=False)
-        kwargs = {k: v for k, v in kwargs.items() if k in ("mode", "num_samples")}
-        return self.actor(obs, **kwargs)
+        kwargs = {k: v for k, v in kwargs.items() if k in ("mode", "num_samples", "aug")}
+        with torch.cuda.device(self.device):
+            return self.actor(obs, **kwargs)
 
     # data-parallel switches keep their names; the all-reduce lives in the engine (dist.py)
     def to_ddp(self, device_ids=None):
@@ -306,6 +307,7 @@ class SAC(BaseAgent):
             self.engine.refresh_alpha()
             self.engine.prime_alpha()
         self.alpha = float(self.log_alpha.exp().item())
+        self._weights_changed()
         return ret
 
     # ------------------------------------------------------------------ the public step
@@ -336,7 +338,13 @@ class SAC(BaseAgent):
             eng.update(updates)
         ret = eng.read_scalars(updates)
         self.alpha = eng._alpha_before
+        self._weights_changed()
         return ret
+
+    def _weights_changed(self):
+        """The rollout path caches the packed MMA images of the PointNet weights: tell it they moved."""
+        pn = self.actor.backbone.visual_nn
+        pn.weights_version = (pn.weights_version or 0) + 1
 
 
 @MFRL.register_module()
@@ -360,5 +368,10 @@ class DrQ(SAC):
     def forward(self, obs, **kwargs):
         """drq.py:33-44: optional inference-time augmentation, then the SAC rollout path."""
         if self.inference_aug is not None:
-            obs = self.inference_aug(GDict(obs).to_torch(device=self.device, wrapper=False))
+            aug = self.inference_aug[0] if len(self.inference_aug) == 1 else None
+            if aug is not None and aug.kind in ("jitter", "rot", "shift"):
+                # fused into the staging kernel of the encode (pcrl_stage_points), like the update path
+                kwargs = dict(kwargs, aug=(AUG_KINDS[aug.kind],) + tuple(aug.params()[1:]))
+            else:
+                obs = self.inference_aug(GDict(obs).to_torch(device=self.device, wrapper=False))
         return super().forward(obs, **kwargs)

@@ -35,6 +35,22 @@ static inline int64_t align_up(int64_t a, int64_t b) { return cdiv(a, b) * b; }
 
 int sm_count();
 
+// Per-device context (pcrl_create / pcrl_destroy): everything the library keeps between calls lives here, one per
+// CUDA device, created on first use or explicitly through the handle API: the SM count, and the internal side stream
+// + fork/join events pcrl_pointnet_bwd runs its weight-gradient GEMMs on.  Nothing is process-global any more.
+struct DeviceCtx {
+  int device = -1;
+  int sms = 0;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+};
+DeviceCtx* device_ctx();  // context of the CURRENT device (lazily created); nullptr + set_error on failure
+
+// TF32 requests that ended on the FFMA kernel because an operand was not TMA-addressable (16-byte base, pitch % 4).
+// pcrl_tf32_fallbacks() reads the count; with pcrl_set_strict_tf32(1) such a call fails instead of falling back.
+void note_tf32_fallback();
+bool strict_tf32();
+
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011), counter-based: no state, graph-replay safe because the
 // per-update counter lives in device memory.

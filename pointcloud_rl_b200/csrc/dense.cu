@@ -48,6 +48,15 @@ int launch_gemm(const GemmArgs& g, int tf32, cudaStream_t st) {
     t.mode = g.accumulate ? (g.split_k > 1 ? 2 : 1) : 0;
     t.k_dev = g.k_dev; t.m_dev = g.m_dev; t.mask = g.mask; t.ldmask = g.ldmask; t.bn_hint = g.bn_hint;
     if (g.K >= 8 && tcg::tc_gemm_supported(t)) return tcg::launch_tc_gemm(t, st);
+    if (g.K >= 8) {
+      // a shape the tensor path is meant for, but an operand is not TMA-addressable (16-byte base, pitch % 4 floats)
+      note_tf32_fallback();
+      if (strict_tf32()) {
+        set_error("tf32 GEMM M=%d N=%d K=%d: operand not TMA-addressable (16-byte base, row pitch %% 4 == 0) and "
+                  "pcrl_set_strict_tf32 is on: refusing the FFMA fallback", g.M, g.N, g.K);
+        return PCRL_EUNSUPPORTED;
+      }
+    }
   }
   return launch_sgemm(g, st);
 }

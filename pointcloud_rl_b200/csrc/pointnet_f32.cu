@@ -590,13 +590,10 @@ int pcrl_pointnet_bwd(const float* xf, int R, int N, int NP, int CP, int C, cons
 
   // The weight-gradient GEMMs only feed the optimizer, the data-gradient chain feeds the next layer: run the
   // wgrads on an internal side stream (event fork/join, graph-capturable) so they overlap the dgrad chain.
-  static cudaStream_t side = nullptr;
-  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  if (!side) {
-    PCRL_CHECK_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
-    PCRL_CHECK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    PCRL_CHECK_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-  }
+  DeviceCtx* ctx = device_ctx();  // the side stream and its events belong to the current device's context
+  if (!ctx) return PCRL_ECUDA;
+  cudaStream_t side = ctx->side;
+  cudaEvent_t ev_fork = ctx->ev_fork, ev_join = ctx->ev_join;
   // 4. layer 2 backward: LN -> dW2 (side), dh1 (main)
   if (!fast && (rc = launch_ln_rows_bwd(w.d2, c3, w.y2hat, w.rstd2, g2, dg2, dbe2, w.d2, c3, A, c3, w.total, st))) return rc;
   PCRL_CHECK_CUDA(cudaEventRecord(ev_fork, st));

@@ -814,12 +814,8 @@ int pcrl_pointnet_fwd_bf16_strided(const void* xh, int R, int src_cloud_stride, 
     return tc2::forward(xh, R, src_cloud_stride, NP, (const char*)wpack + wpack1_bytes(c1, c2, c3), c1, c2, c3, ln_eps,
                         pool_keys, pooled, argmax, st);
   const tc::SmemLayout L = tc::make_layout(c1, c2, c3);
-  static bool attr_set = false;
-  if (!attr_set) {
-    PCRL_CHECK_CUDA(cudaFuncSetAttribute(tc::pointnet_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024));
-    attr_set = true;
-  }
+  PCRL_CHECK_CUDA(cudaFuncSetAttribute(tc::pointnet_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       227 * 1024));
   const int tiles_per_cloud = NP / 128;
   const int n_tiles = R * tiles_per_cloud;
   const int grid = std::min(sm_count(), n_tiles);

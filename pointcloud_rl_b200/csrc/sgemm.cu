@@ -3,6 +3,9 @@
 // Tensor-core (tcgen05) kernels live in pointnet_tc.cu.
 #include <stdarg.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace pcrl {
@@ -16,15 +19,46 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 
-int sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) cached = 148;
+// ---- per-device contexts ------------------------------------------------------------------------
+static std::mutex g_ctx_mutex;
+static DeviceCtx* g_ctx[64] = {nullptr};
+static std::atomic<long long> g_tf32_fallbacks{0};
+static std::atomic<int> g_strict_tf32{0};
+
+static DeviceCtx* make_ctx(int dev) {
+  auto* c = new DeviceCtx();
+  c->device = dev;
+  if (cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) c->sms = 148;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  if (cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, lo) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    set_error("pcrl: could not create the device context of device %d: %s", dev, cudaGetErrorString(cudaGetLastError()));
+    delete c;
+    return nullptr;
   }
-  return cached;
+  return c;
 }
+
+DeviceCtx* device_ctx() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    set_error("pcrl: no current CUDA device");
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> lock(g_ctx_mutex);
+  if (!g_ctx[dev]) g_ctx[dev] = make_ctx(dev);
+  return g_ctx[dev];
+}
+
+int sm_count() {
+  DeviceCtx* c = device_ctx();
+  return c ? c->sms : 148;
+}
+
+void note_tf32_fallback() { g_tf32_fallbacks.fetch_add(1); }
+bool strict_tf32() { return g_strict_tf32.load() != 0; }
 
 constexpr int BM = 64, BN = 64, BK = 16, PAD = 4;
 
@@ -148,4 +182,42 @@ extern "C" {
 int pcrl_abi_version(void) { return PCRL_ABI_VERSION; }
 const char* pcrl_last_error(void) { return pcrl::last_error(); }
 int pcrl_sm_count(void) { return pcrl::sm_count(); }
+
+int64_t pcrl_create(int device) {
+  int prev = 0;
+  if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) {
+    pcrl::set_error("pcrl_create: cannot select device %d", device);
+    return 0;
+  }
+  pcrl::DeviceCtx* c = pcrl::device_ctx();
+  cudaSetDevice(prev);
+  return (int64_t)reinterpret_cast<intptr_t>(c);
+}
+
+int pcrl_destroy(int64_t handle) {
+  auto* c = reinterpret_cast<pcrl::DeviceCtx*>((intptr_t)handle);
+  if (!c) return PCRL_OK;
+  std::lock_guard<std::mutex> lock(pcrl::g_ctx_mutex);
+  if (c->device < 0 || c->device >= 64 || pcrl::g_ctx[c->device] != c) {
+    pcrl::set_error("pcrl_destroy: not a live handle");
+    return PCRL_EINVAL;
+  }
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->side);
+  cudaStreamDestroy(c->side);
+  cudaEventDestroy(c->ev_fork);
+  cudaEventDestroy(c->ev_join);
+  cudaSetDevice(prev);
+  pcrl::g_ctx[c->device] = nullptr;
+  delete c;
+  return PCRL_OK;
+}
+
+int64_t pcrl_tf32_fallbacks(void) { return (int64_t)pcrl::g_tf32_fallbacks.load(); }
+int pcrl_set_strict_tf32(int on) {
+  pcrl::g_strict_tf32.store(on ? 1 : 0);
+  return PCRL_OK;
+}
 }

@@ -578,11 +578,8 @@ int launch_tc_gemm(const TcGemmArgs& g, cudaStream_t st) {
       set_error("tc_gemm: cuTensorMapEncodeTiled failed");
       return PCRL_ECUDA;
     }
-    static bool attr_c = false;
-    if (!attr_c) {
-      PCRL_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr_c = true;
-    }
+    // function attributes are per device: set on every launch (host-side, ~1 us) instead of behind a process-wide flag
+    PCRL_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(mt * cdiv(g.N, bn) * cluster_k), 1, 1);
     cfg.blockDim = dim3(kThreads, 1, 1);
@@ -622,11 +619,7 @@ int launch_tc_gemm(const TcGemmArgs& g, cudaStream_t st) {
     set_error("tc_gemm: cuTensorMapEncodeTiled failed");
     return PCRL_ECUDA;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    PCRL_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  PCRL_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)sms * ctas_per_sm);
   tc_gemm_kernel<256><<<grid, kThreads, smem, st>>>(ma, mb, P);
   PCRL_CHECK_LAUNCH();

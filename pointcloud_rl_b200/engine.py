@@ -167,6 +167,12 @@ class UpdateEngine:
         self.seed = int(seed)
         self.layout = ParamLayout(spec)
         dev = self.device
+        if dev.type == "cuda":
+            # the library's per-device context (SM count, the backward's internal side stream + events): created here,
+            # explicitly, rather than on first use inside a kernel call
+            self.ctx = int(self.L.create(dev.index if dev.index is not None else torch.cuda.current_device()))
+            if not self.ctx:
+                raise RuntimeError(f"pcrl_create failed: {self.L.last_error()}")
         f32 = dict(dtype=torch.float32, device=dev)
         self.params = torch.zeros(self.layout.total, **f32)
         self.grads = torch.zeros(self.layout.trainable, **f32)

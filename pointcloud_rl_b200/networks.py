@@ -190,8 +190,11 @@ class KernelRunner:
             self._ws[key] = ws
         return ws
 
-    def encode(self, spec: PathSpec, p: Dict[str, torch.Tensor], obs: Dict[str, torch.Tensor], out=None, aug=None):
-        """obs: device tensors xyz [B,3,N] f32, rgb [B,3,N] u8|f32, pos_encoding [B,F,N] u8, seg [B,K,N] bool/u8."""
+    def encode(self, spec: PathSpec, p: Dict[str, torch.Tensor], obs: Dict[str, torch.Tensor], out=None, aug=None,
+               weights_version=None):
+        """obs: device tensors xyz [B,3,N] f32, rgb [B,3,N] u8|f32, pos_encoding [B,F,N] u8, seg [B,K,N] bool/u8.
+        weights_version: an integer the owner bumps whenever the PointNet weights change; the packed MMA images are then
+        rebuilt only on a change (None = unknown: rebuilt on every call)."""
         L, st = lib(), stream_ptr()
         xyz = obs["xyz"].contiguous().float()
         B, device = xyz.shape[0], xyz.device
@@ -215,8 +218,11 @@ class KernelRunner:
         if kind:
             self._counter.add_(1)
         if self.precision == "bf16":
-            L.pointnet_pack_weights(p["pn.w0"], p["pn.b0"], p["pn.w1"], p["pn.g1"], p["pn.be1"], p["pn.w2"],
-                                    p["pn.g2"], p["pn.be2"], spec.C, c1, c2, c3, int(rgb_u8), ws["wpack"], st)
+            tag = (weights_version, int(rgb_u8))
+            if weights_version is None or ws.get("packed") != tag:
+                L.pointnet_pack_weights_part(p["pn.w0"], p["pn.b0"], p["pn.w1"], p["pn.g1"], p["pn.be1"], p["pn.w2"],
+                                             p["pn.g2"], p["pn.be2"], spec.C, c1, c2, c3, int(rgb_u8), 1, ws["wpack"], st)
+                ws["packed"] = tag
             L.pointnet_fwd_bf16(ws["xh"], B, spec.n_points, spec.NP, ws["wpack"], c1, c2, c3, spec.ln_eps, ws["keys"],
                                 ws["pooled"], None, st)
         else:
@@ -226,7 +232,9 @@ class KernelRunner:
                 ws["scratch"], ws["fwd_bytes"], st)
         D = spec.out_dim
         if out is None:
-            out = torch.empty(B, D, dtype=torch.float32, device=device)
+            out = ws.get("out")
+            if out is None:
+                out = ws["out"] = torch.empty(B, D, dtype=torch.float32, device=device)
         L.linear_fwd(ws["pooled"], c3, p["pn.wf"], p["pn.bf"], ws["z"], D, B, c3, D, 0, self.tf32, st)
         L.layernorm_fwd(ws["z"], p["pn.gf"], p["pn.bef"], out, out.stride(0), None, None, B, D, spec.head_ln_eps, st)
         self.calls += 1
@@ -236,9 +244,11 @@ class KernelRunner:
         L, st = lib(), stream_ptr()
         M, dev = x.shape[0], x.device
         h1n, h2n = p[f"{net}.w0"].shape[0], p[f"{net}.w1"].shape[0]
-        h1 = torch.empty(M, h1n, dtype=torch.float32, device=dev)
-        h2 = torch.empty(M, h2n, dtype=torch.float32, device=dev)
-        out = torch.empty(M, nout, dtype=torch.float32, device=dev)
+        key = ("mlp", M, h1n, h2n, nout, str(dev))
+        bufs = self._ws.get(key)
+        if bufs is None:  # activations of the rollout MLP: allocated once per batch size
+            bufs = self._ws[key] = tuple(torch.empty(M, n, dtype=torch.float32, device=dev) for n in (h1n, h2n, nout))
+        h1, h2, out = bufs
         L.linear_fwd(x, x.stride(0), p[f"{net}.w0"], p[f"{net}.b0"], h1, h1n, M, K, h1n, 1, self.tf32, st)
         L.linear_fwd(h1, h1n, p[f"{net}.w1"], p[f"{net}.b1"], h2, h2n, M, h1n, h2n, 1, self.tf32, st)
         L.linear_fwd(h2, h2n, p[f"{net}.w2"], p[f"{net}.b2"], out, nout, M, h2n, nout, 0, self.tf32, st)
@@ -284,6 +294,7 @@ class PointNet(ExtendedModule):
         self.final_mlp = nn.Sequential(nn.Linear(self.mlp_spec[-1], self.out_channels), nn.LayerNorm(self.out_channels))
         self.precision = precision
         self._runner = None
+        self.weights_version = None  # the owning agent counts weight changes here (None: unknown, re-pack every call)
 
     def spec_for(self, n_points, n_pos=0, n_seg=0, has_rgb=True, rgb_u8=True, **extra):
         return PathSpec(n_points=n_points, action_dim=extra.get("action_dim", 1), state_dim=extra.get("state_dim", 0),
@@ -308,7 +319,7 @@ class PointNet(ExtendedModule):
             raise ValueError(f"observation has {spec.C} channels, PointNet was built with feat_dim={self.feat_dim}")
         if self._runner is None or self._runner.precision != self.precision:
             self._runner = KernelRunner(self.precision)
-        return self._runner.encode(spec, _pn_views(self), obs, aug=aug)
+        return self._runner.encode(spec, _pn_views(self), obs, aug=aug, weights_version=self.weights_version).clone()
 
 
 @NETWORK.register_module()
@@ -328,7 +339,7 @@ class Visuomotor(ExtendedModule):
 
     @torch.no_grad()
     def forward(self, obs, actions=None, feature=None, visual_feature=None, save_feature=False, detach_visual=False,
-                with_robot_state=True, **kwargs):
+                with_robot_state=True, aug=None, **kwargs):
         assert isinstance(obs, dict), f"obs is not a dict! {type(obs)}"
         obs = dict(obs)
         robot_state = None
@@ -337,7 +348,7 @@ class Visuomotor(ExtendedModule):
                 assert robot_state is None, "Please provide only one robot state!"
                 robot_state = torch.as_tensor(obs.pop(key)).to(self.device, torch.float32)
         if feature is None:
-            feat = self.visual_nn(obs) if visual_feature is None else visual_feature
+            feat = self.visual_nn(obs, aug=aug) if visual_feature is None else visual_feature
             if save_feature or visual_feature is not None:
                 self.saved_visual_feature = feat.clone()
             if robot_state is not None and with_robot_state:
@@ -351,7 +362,7 @@ class Visuomotor(ExtendedModule):
         feat = feat.contiguous()
         runner = self.visual_nn._runner or KernelRunner(self.visual_nn.precision)
         p = _mlp_views(self.final_mlp, "m")
-        return runner.mlp3(p, "m", feat, feat.shape[1], self.final_mlp.mlp_spec[-1])
+        return runner.mlp3(p, "m", feat, feat.shape[1], self.final_mlp.mlp_spec[-1]).clone()
 
 
 @REGRESSION.register_module()
@@ -414,7 +425,7 @@ class ActorCriticBase(ExtendedModule):
     def forward(self, obs, actions=None, **kwargs):
         head_kwargs = {k: kwargs.pop(k) for k in ("mode", "num_samples") if k in kwargs}
         feature = self.backbone(obs, actions, **{k: v for k, v in kwargs.items()
-                                                 if k in ("feature", "visual_feature", "save_feature", "detach_visual")})
+                                                 if k in ("feature", "visual_feature", "save_feature", "detach_visual", "aug")})
         return self.head(feature, **head_kwargs) if self.head is not None else feature
 
 

@@ -124,6 +124,51 @@ def gen_update_fixture(ns, name, cfg_path, algo, aug, aug_rng, B, N, A, n_seg, n
     print(name, "ok:", {k: round(v, 5) for k, v in ret.items()})
 
 
+def gen_checkpoint_fixture(ns, name="ref_checkpoint_drq_small"):
+    """A checkpoint written by the REFERENCE's own save_checkpoint (checkpoint_utils.py:238-266) after two updates of the
+    tiny DrQ jitter configuration, plus -- for the test's cross-check -- every parameter's Adam moments keyed by the
+    parameter's NAME (found by object identity between optimizer.param_groups and named_parameters), and the inputs
+    and the reference's returned scalars of a third update taken from the saved state."""
+    from pyrl.utils.torch.checkpoint_utils import save_checkpoint
+
+    g = dict(np.load(os.path.join(OUT, "drq_jitter_small.npz")))
+    meta = {k.split("/")[1]: g[k].item() for k in g if k.startswith("meta/")}
+    B, N, A, S = meta["B"], meta["N"], meta["A"], meta["S"]
+    batch = O.synthetic_batch(seed=0, B=B, N=N, A=A, n_seg=meta["n_seg"], n_pos=0, state_dim=S, duplicate_tail=True)
+    overrides = {
+        "batch_size": B,
+        "actor_cfg.nn_cfg.mlp_cfg.mlp_spec": ["128 + agent_shape", HIDDEN, HIDDEN, "action_shape * 2"],
+        "critic_cfg.nn_cfg.mlp_cfg.mlp_spec": ["128 + agent_shape + action_shape", HIDDEN, HIDDEN, 1],
+    }
+    torch.manual_seed(0)
+    agent, _ = build_reference_agent(ns, "configs/mfrl/drq/maniskill/pn_jitter.py", obs_shape_of(batch["obs"]), A, overrides)
+    mem = FakeMemory(ns, batch)
+    for u in (1, 2):
+        torch.manual_seed(1000 + u)
+        agent.update_parameters(mem, updates=u)
+    path = os.path.join(OUT, name + ".ckpt")
+    save_checkpoint(agent, path, meta={"updates": 2})
+    out = {}
+    names = {id(p): n for n, p in agent.named_parameters()}
+    for opt_name in ("actor_optim", "critic_optim", "alpha_optim"):
+        opt = getattr(agent, opt_name)
+        for grp in opt.param_groups:
+            for prm in grp["params"]:
+                st = opt.state[prm]
+                out[f"adam/{opt_name}/{names[id(prm)]}/m"] = st["exp_avg"].detach().numpy().copy()
+                out[f"adam/{opt_name}/{names[id(prm)]}/v"] = st["exp_avg_sq"].detach().numpy().copy()
+                out[f"adam/{opt_name}/{names[id(prm)]}/step"] = np.float64(float(st["step"]))
+    flatten("params/", O.params_from_reference_state_dict(agent.state_dict()), out)
+    noise = draw_noise(1003, "drq", "jitter", 2, B, N, A, False, (-0.01, 0.01))
+    flatten("noise3/", noise, out)
+    torch.manual_seed(1003)
+    ret = agent.update_parameters(mem, updates=3)
+    for key, val in ret.items():
+        out[f"ret3/{key}"] = np.float64(val)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "ok:", os.path.getsize(path), "bytes;", {k: round(v, 5) for k, v in ret.items()})
+
+
 def gen_pointnet_fixture(ns, name, C_extra, B, N, dup, widths=(128, 128, 256), D=128):
     """PointNet forward through the reference's NETWORK registry (pointnet.py), hooks capture the
     ConvMLP output so pooled values + argmax (h.max(-1)) are recorded too."""
@@ -163,6 +208,9 @@ def main():
     if "--only-downsample" in sys.argv:  # added after the other fixtures were committed; they are not regenerated
         gen_update_fixture(ns, "drq_downsample_small", "configs/mfrl/drq/maniskill/pn_dropout.py", "drq", "downsample",
                            (0.3, 0), B=5, N=80, A=4, n_seg=2, n_pos=0, S=9, dup=False)
+        return
+    if "--only-checkpoint" in sys.argv:
+        gen_checkpoint_fixture(ns)
         return
     if "--only-colorjitter" in sys.argv:  # added in round 2; the other fixtures are not regenerated
         gen_update_fixture(ns, "drq_colorjitter_small", "configs/mfrl/drq/maniskill/pn_colorjitter.py", "drq", "colorjitter",

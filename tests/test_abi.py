@@ -10,7 +10,9 @@ def test_header_declares_expected_entry_points():
     for name in ("pcrl_stage_points", "pcrl_pointnet_fwd_f32", "pcrl_pointnet_fwd_bf16", "pcrl_pointnet_pack_weights",
                  "pcrl_pointnet_bwd", "pcrl_linear_fwd", "pcrl_linear_bwd", "pcrl_layernorm_fwd", "pcrl_layernorm_bwd",
                  "pcrl_tanh_gaussian_fwd", "pcrl_tanh_gaussian_bwd", "pcrl_td_target", "pcrl_critic_loss",
-                 "pcrl_actor_loss", "pcrl_adam_step", "pcrl_polyak"):
+                 "pcrl_actor_loss", "pcrl_adam_step", "pcrl_polyak", "pcrl_create", "pcrl_destroy", "pcrl_tf32_fallbacks",
+                 "pcrl_set_strict_tf32", "pcrl_pointnet_fwd_tf32", "pcrl_pointnet_pack_weights_part",
+                 "pcrl_color_jitter_points"):
         assert name in protos, name
     # plain-C signatures only: pointers, fixed-width ints, floats
     for name, (_, args) in protos.items():

@@ -223,3 +223,105 @@ def test_widened_augmentation_configs_run_through_the_public_call(rel):
         out = agent.update_parameters(mem, u)
         assert all(np.isfinite(v) for v in out.values())
     assert {"drq/critic_loss", "drq/actor_loss", "drq/alpha_loss", "drq/entropy"} <= set(out)
+
+
+@pytest.mark.gpu
+def test_reference_written_checkpoint_loads_and_training_continues(tmp_path):
+    """a .ckpt written by the REFERENCE's save_checkpoint (checkpoint_utils.py:238-266, parameters
+    + the three torch Adam state dicts under `actor_optim` / `critic_optim` / `alpha_optim`) loads into the agent --
+    weights, per-tensor Adam moments (cross-checked by parameter NAME against what the reference held) and step
+    counts -- and the next update reproduces the reference's own third update.  Then the agent's save_checkpoint
+    writes the same layout back."""
+    from oracle import pointnet_sac_oracle as O
+    from pointcloud_rl_b200.checkpoint import load_checkpoint, save_checkpoint
+
+    g = load_golden("ref_checkpoint_drq_small")
+    jg = load_golden("drq_jitter_small")
+    m = {k: v.item() for k, v in jg["meta"].items()}
+    batch = {k: (dict(v) if isinstance(v, dict) else v) for k, v in jg["batch"].items()}
+    obs_shape = {k: (list(v.shape[1:]) if v.ndim > 2 else int(v.shape[1])) for k, v in batch["obs"].items()}
+    torch.manual_seed(123)  # different initial weights: everything must come from the file
+    agent = make_agent("mfrl/drq/maniskill/pn_jitter.py", obs_shape, m["A"], hidden=64, batch_size=m["B"], precision="fp32",
+                       use_cuda_graph=False).to("cuda")
+    path = os.path.join(GOLDEN, "ref_checkpoint_drq_small.ckpt")
+    ck = load_checkpoint(agent, path, sample=batch)
+    assert ck["meta"] == {"updates": 2}
+    eng = agent.engine
+    for ours, val in g["params"].items():
+        assert torch.allclose(eng.p[ours].cpu(), torch.from_numpy(val).reshape(eng.p[ours].shape), atol=0), ours
+    mviews, vviews = eng.layout.views(eng.adam_m), eng.layout.views(eng.adam_v)
+    steps = eng.steps.cpu().tolist()
+    checked = 0
+    for ours, ref_name in O.reference_key_map().items():
+        for idx, opt in enumerate(("critic_optim", "actor_optim", "alpha_optim")):
+            entry = g["adam"][opt].get(ref_name)
+            if entry is None:
+                continue
+            assert torch.equal(mviews[ours].cpu().flatten(), torch.from_numpy(entry["m"]).flatten()), (opt, ours)
+            assert torch.equal(vviews[ours].cpu().flatten(), torch.from_numpy(entry["v"]).flatten()), (opt, ours)
+            assert steps[idx] == int(entry["step"]), (opt, steps, entry["step"])
+            checked += 1
+    assert checked == 24 + 6 + 1  # every tensor of the three optimizers (optimizer_utils.py:31-64: one group per tensor)
+    # the reference's third update, from the loaded state
+    noise = {k: torch.from_numpy(v).cuda() for k, v in g["noise3"].items()}
+    eng.upload_batch(batch)
+    eng.update(3, noise)
+    ret = eng.read_scalars(3)
+    ref = {f"{a}/{b}": float(v) for a, sub in g["ret3"].items() for b, v in sub.items()}
+    assert set(ret) == set(ref)
+    for key, val in ref.items():
+        assert ret[key] == pytest.approx(val, rel=1e-3, abs=1e-4), key
+    # and back: same keys, optimizer entries in torch.optim.Adam's layout
+    out = tmp_path / "ours.ckpt"
+    save_checkpoint(agent, out, meta={"updates": 3})
+    ours_ck = torch.load(out, map_location="cpu", weights_only=True)
+    assert set(ours_ck["state_dict"]) == set(ck["state_dict"])
+    for opt in ("actor_optim", "critic_optim", "alpha_optim"):
+        a, b = ours_ck["state_dict"][opt], ck["state_dict"][opt]
+        assert len(a["param_groups"]) == len(b["param_groups"]) and set(a["state"]) == set(b["state"])
+        assert [grp["params"] for grp in a["param_groups"]] == [grp["params"] for grp in b["param_groups"]]
+        for i in a["state"]:
+            assert a["state"][i]["exp_avg"].shape == b["state"][i]["exp_avg"].shape
+
+
+@pytest.mark.gpu
+def test_rollout_path_bf16_cached_weights_and_fused_inference_aug():
+    """SURVEY.md section 8f.4 (BaseAgent.forward, module_utils.py:147-159; DrQ.forward, drq.py:33-44) at the agent's
+    precision: bf16 rollout features within 2e-2 of the oracle; the packed weight images are cached between calls and
+    rebuilt after an update; inference_aug="same" runs the jitter inside the staging kernel."""
+    from oracle import pointnet_sac_oracle as O
+    from pointcloud_rl_b200.data import FixedBatchMemory
+    from pointcloud_rl_b200.synthetic import synthetic_batch
+
+    N, A, S = 300, 5, 13
+    obs_shape = {"xyz": [3, N], "rgb": [3, N], "seg": [1, N], "agent": S}
+    agent = make_agent("mfrl/drq/maniskill/pn_jitter.py", obs_shape, A, hidden=64, batch_size=4, precision="bf16").to("cuda")
+    rs = np.random.RandomState(1)
+    obs = O.synthetic_obs(rs, 3, N, n_seg=1, state_dim=S)
+
+    def oracle_mean():
+        sd = {k: v.detach().cpu() for k, v in agent.state_dict().items()}
+        p = O.params_from_reference_state_dict(sd)
+        f = O.pointnet_forward(p, O.preprocess({k: torch.from_numpy(v) for k, v in obs.items() if k != "agent"}))
+        return torch.tanh(O.mlp3(p, "actor", torch.cat([f, torch.from_numpy(obs["agent"])], -1))[:, :A])
+
+    pn = agent.actor.backbone.visual_nn
+    mean = agent(obs, mode="eval")
+    assert float((mean.cpu() - oracle_mean()).abs().max()) < 2e-2
+    runner, calls0 = pn._runner, agent.engine.L.launches if agent.engine else None
+    n0 = runner.L.launches
+    agent(obs, mode="eval")
+    per_call_cached = runner.L.launches - n0
+    mem = FixedBatchMemory(synthetic_batch(0, 4, N, A, n_seg=1, state_dim=S))
+    agent.update_parameters(mem, 1)  # weights move -> the cached images are stale
+    n0 = runner.L.launches
+    mean2 = agent(obs, mode="eval")
+    assert runner.L.launches - n0 == per_call_cached + 1  # exactly one extra C-ABI call: the re-pack
+    assert float((mean2.cpu() - oracle_mean()).abs().max()) < 2e-2
+    assert not torch.equal(mean, mean2)
+    # inference-time augmentation fused into the staging kernel
+    aug_agent = make_agent("mfrl/drq/maniskill/pn_jitter.py", obs_shape, A, hidden=64, batch_size=4, precision="bf16",
+                           inference_aug="same").to("cuda")
+    a1, a2 = aug_agent(obs, mode="eval"), aug_agent(obs, mode="eval")
+    assert a1.shape == (3, A) and torch.isfinite(a1).all() and not torch.equal(a1, a2)  # fresh jitter every call
+    assert float((a1 - a2).abs().max()) < 0.2

@@ -174,3 +174,26 @@ def test_checkpoint_round_trip_through_the_agent_api(tmp_path):
     for ref, got in ((ref3, got3), (ref4, got4)):
         for key in ref:
             assert got[key] == pytest.approx(ref[key], rel=1e-5, abs=1e-6), key
+
+
+def test_device_context_handle_and_strict_tf32():
+    """pcrl_create / pcrl_destroy own the per-device state (no process-global streams or flags); with
+    pcrl_set_strict_tf32 a tf32 GEMM whose operands are not TMA-addressable fails instead of silently running on FFMA."""
+    from pointcloud_rl_b200._lib import PcrlError, lib, stream_ptr
+
+    L = lib()
+    h = int(L.create(0))
+    assert h != 0 and int(L.create(0)) == h  # one context per device, idempotent
+    assert L.sm_count() >= 100
+    M, K, N = 64, 67, 32  # row pitch 67 floats: not a multiple of 16 bytes -> no TMA descriptor
+    x, w, y = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda"), torch.empty(M, N, device="cuda")
+    before = int(L.tf32_fallbacks())
+    L.linear_fwd(x, K, w, None, y, N, M, K, N, 0, 1, stream_ptr())  # permissive: exact FFMA result, counted
+    assert int(L.tf32_fallbacks()) == before + 1
+    assert torch.allclose(y, x @ w.t(), atol=1e-4)
+    L.set_strict_tf32(1)
+    try:
+        with pytest.raises(PcrlError, match="not TMA-addressable"):
+            L.linear_fwd(x, K, w, None, y, N, M, K, N, 0, 1, stream_ptr())
+    finally:
+        L.set_strict_tf32(0)
