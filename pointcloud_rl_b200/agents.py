@@ -64,8 +64,10 @@ class FlatAdam:
         if eng is not None:
             m, v = eng.layout.views(eng.adam_m), eng.layout.views(eng.adam_v)
             step = float(eng.steps[self.step_index].item())
+            shapes = {k: shp for k, (_, shp) in self.agent._module_params().items()}  # Conv1d weights are [c, C, 1]
             for i, n in enumerate(self.names):
-                state[i] = {"step": torch.tensor(step), "exp_avg": m[n].clone(), "exp_avg_sq": v[n].clone()}
+                state[i] = {"step": torch.tensor(step), "exp_avg": m[n].clone().reshape(shapes[n]),
+                            "exp_avg_sq": v[n].clone().reshape(shapes[n])}
         return {"state": state, "param_groups": self.param_groups}
 
     def load_state_dict(self, sd):
@@ -109,11 +111,51 @@ class BaseAgent(ExtendedModule):
 
     @torch.no_grad()
     def forward(self, obs, **kwargs):
-        """Rollout entry (module_utils.py:147-159): obs -> device -> actor(obs, mode=...)."""
-        obs = GDict(obs).to_torch(device=self.device, non_blocking=True, wrapper=False)
+        """Rollout entry (module_utils.py:147-159): obs -> device -> actor(obs, mode=...).  With use_cuda_graph the
+        ~15 kernels of one rollout step (stage, fused encode, head, actor MLP, tanh-Gaussian sample) replay from a CUDA
+        graph per (batch size, mode): the observation is copied into the graph's static input buffers."""
         kwargs = {k: v for k, v in kwargs.items() if k in ("mode", "num_samples", "aug")}
         with torch.cuda.device(self.device):
+            if getattr(self, "use_cuda_graph", False) and self.device.type == "cuda":
+                return self._forward_graphed(obs, kwargs)
+            obs = GDict(obs).to_torch(device=self.device, non_blocking=True, wrapper=False)
             return self.actor(obs, **kwargs)
+
+    def _forward_graphed(self, obs, kwargs):
+        obs = unwrap(obs)
+        flat = {k: torch.as_tensor(v) for k, v in obs.items()}
+        pn = self.actor.backbone.visual_nn
+        # parameter storage is part of the key: the first update re-points the module parameters into the engine's flat
+        # buffer (and .to() moves them), which would leave a captured graph reading the old tensors
+        key = (tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(flat.items())), kwargs.get("mode", "explore"),
+               repr(kwargs.get("aug")), self.actor.backbone.final_mlp.mlp.linear0.weight.data_ptr(),
+               pn.conv.mlp.conv0.weight.data_ptr())
+        cache = self.__dict__.setdefault("_rollout_graphs", {})
+        entry = cache.get(key)
+        if entry is None:
+            static = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in flat.items()}
+            for k, v in flat.items():
+                static[k].copy_(v, non_blocking=True)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):  # warm-up: workspaces, module loading, the packed weight images
+                for _ in range(2):
+                    self.actor(dict(static), **kwargs)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.actor(dict(static), **kwargs)
+            entry = cache[key] = dict(static=static, graph=graph, out=out, version=pn.weights_version)
+        for k, v in flat.items():
+            entry["static"][k].copy_(v, non_blocking=True)
+        if entry["version"] != pn.weights_version:
+            # the packed MMA images of the PointNet weights are graph-external state: refresh them eagerly
+            pn.repack()
+            entry["version"] = pn.weights_version
+        entry["graph"].replay()
+        out = entry["out"]
+        return [o.clone() for o in out] if isinstance(out, (list, tuple)) else out.clone()
 
     # data-parallel switches keep their names; the all-reduce lives in the engine (dist.py)
     def to_ddp(self, device_ids=None):
@@ -215,6 +257,7 @@ class SAC(BaseAgent):
             raise NotImplementedError("the three optimizers must share one Adam eps")
         self._aug = None
         self._num_aug = 1
+        self.actor.backbone.visual_nn.weights_version = 0  # this agent owns the weights and counts their changes
 
     # ------------------------------------------------------------------ engine plumbing
     def _named_views(self):

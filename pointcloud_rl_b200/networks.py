@@ -240,6 +240,16 @@ class KernelRunner:
         self.calls += 1
         return out
 
+    def repack(self, p, weights_version):
+        L, st = lib(), stream_ptr()
+        for key, ws in self._ws.items():
+            if isinstance(ws, dict) and "wpack" in ws and "packed" in ws:
+                spec_c, (c1, c2, c3) = key[2], key[3]
+                rgb_u8 = ws["packed"][1]
+                L.pointnet_pack_weights_part(p["pn.w0"], p["pn.b0"], p["pn.w1"], p["pn.g1"], p["pn.be1"], p["pn.w2"],
+                                             p["pn.g2"], p["pn.be2"], spec_c, c1, c2, c3, rgb_u8, 1, ws["wpack"], st)
+                ws["packed"] = (weights_version, rgb_u8)
+
     def mlp3(self, p, net, x, K, nout):
         L, st = lib(), stream_ptr()
         M, dev = x.shape[0], x.device
@@ -295,6 +305,12 @@ class PointNet(ExtendedModule):
         self.precision = precision
         self._runner = None
         self.weights_version = None  # the owning agent counts weight changes here (None: unknown, re-pack every call)
+
+    def repack(self):
+        """Rebuild the cached MMA weight images of every workspace now (used before replaying a captured rollout graph,
+        where the per-call version check is not part of the graph)."""
+        if self._runner is not None:
+            self._runner.repack(_pn_views(self), self.weights_version)
 
     def spec_for(self, n_points, n_pos=0, n_seg=0, has_rgb=True, rgb_u8=True, **extra):
         return PathSpec(n_points=n_points, action_dim=extra.get("action_dim", 1), state_dim=extra.get("state_dim", 0),

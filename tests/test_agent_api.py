@@ -295,7 +295,8 @@ def test_rollout_path_bf16_cached_weights_and_fused_inference_aug():
 
     N, A, S = 300, 5, 13
     obs_shape = {"xyz": [3, N], "rgb": [3, N], "seg": [1, N], "agent": S}
-    agent = make_agent("mfrl/drq/maniskill/pn_jitter.py", obs_shape, A, hidden=64, batch_size=4, precision="bf16").to("cuda")
+    agent = make_agent("mfrl/drq/maniskill/pn_jitter.py", obs_shape, A, hidden=64, batch_size=4, precision="bf16",
+                       use_cuda_graph=False).to("cuda")
     rs = np.random.RandomState(1)
     obs = O.synthetic_obs(rs, 3, N, n_seg=1, state_dim=S)
 
@@ -308,7 +309,7 @@ def test_rollout_path_bf16_cached_weights_and_fused_inference_aug():
     pn = agent.actor.backbone.visual_nn
     mean = agent(obs, mode="eval")
     assert float((mean.cpu() - oracle_mean()).abs().max()) < 2e-2
-    runner, calls0 = pn._runner, agent.engine.L.launches if agent.engine else None
+    runner = pn._runner
     n0 = runner.L.launches
     agent(obs, mode="eval")
     per_call_cached = runner.L.launches - n0
@@ -321,7 +322,19 @@ def test_rollout_path_bf16_cached_weights_and_fused_inference_aug():
     assert not torch.equal(mean, mean2)
     # inference-time augmentation fused into the staging kernel
     aug_agent = make_agent("mfrl/drq/maniskill/pn_jitter.py", obs_shape, A, hidden=64, batch_size=4, precision="bf16",
-                           inference_aug="same").to("cuda")
+                           inference_aug="same", use_cuda_graph=False).to("cuda")
     a1, a2 = aug_agent(obs, mode="eval"), aug_agent(obs, mode="eval")
     assert a1.shape == (3, A) and torch.isfinite(a1).all() and not torch.equal(a1, a2)  # fresh jitter every call
     assert float((a1 - a2).abs().max()) < 0.2
+    # CUDA-graph replay of the rollout step (the default): same numbers as the eager path, tracks weight updates
+    g_agent = make_agent("mfrl/drq/maniskill/pn_jitter.py", obs_shape, A, hidden=64, batch_size=4, precision="bf16").to("cuda")
+    g_agent.load_state_dict(agent.state_dict())
+    assert torch.equal(g_agent(obs, mode="eval"), agent(obs, mode="eval"))
+    assert torch.equal(g_agent(obs, mode="eval"), agent(obs, mode="eval"))  # second call = replay
+    g_agent.update_parameters(mem, 1)
+    agent2 = make_agent("mfrl/drq/maniskill/pn_jitter.py", obs_shape, A, hidden=64, batch_size=4, precision="bf16",
+                        use_cuda_graph=False).to("cuda")
+    agent2.load_state_dict(g_agent.state_dict())
+    assert torch.equal(g_agent(obs, mode="eval"), agent2(obs, mode="eval"))  # replay sees the updated weights
+    s1, s2 = g_agent(obs, mode="explore"), g_agent(obs, mode="explore")
+    assert not torch.equal(s1, s2)  # the Philox counter advances inside the graph
