@@ -60,6 +60,14 @@ def main():
     broadcast_state(part)
     part.upload_batch(shard(g["batch"], rank, world))
     for u in range(1, m["n_updates"] + 1):
+        # every update starts from the single-process engine's state on all ranks: in the reduced-precision tier the two
+        # trajectories would otherwise drift apart through Adam (|delta w| ~ lr whatever the gradient's size), which
+        # says nothing about the all-reduce
+        for dst, src in ((part.params, whole.params), (part.adam_m, whole.adam_m), (part.adam_v, whole.adam_v),
+                         (part.steps, whole.steps), (part.counter, whole.counter)):
+            dst.copy_(src)
+        part.refresh_alpha()
+        part.prime_alpha()
         noise = {k: torch.from_numpy(np.asarray(v)) for k, v in g[f"noise{u}"].items()}
         whole.update(u, {k: v.to(dev) for k, v in noise.items()})
         mine = {k: v.to(dev) for k, v in shard(noise, rank, world).items()}
@@ -78,8 +86,8 @@ def main():
         lo, hi = part.layout.group_range["critic"]
         gsum = part.grads[lo:hi] / world
         dg = float((gsum - whole.grads[lo:hi]).norm() / whole.grads[lo:hi].norm())
-        tol_g = 1e-4 if precision == "fp32" else 2e-2
-        good = same and dg < tol_g and dp < (1e-4 if precision == "fp32" else 5e-3)
+        tol_g = 1e-4 if precision == "fp32" else 1e-3  # same kernels on the same clouds: only summation order differs
+        good = same and dg < tol_g and dp < (1e-4 if precision == "fp32" else 1e-3)
         if not good:
             print(f"[rank {rank}] update {u}: identical={same} grad_rel={dg:.2e} param_rel={dp:.2e}", flush=True)
         ok = ok and good
