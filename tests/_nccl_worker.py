@@ -66,8 +66,9 @@ def main():
         for dst, src in ((part.params, whole.params), (part.adam_m, whole.adam_m), (part.adam_v, whole.adam_v),
                          (part.steps, whole.steps), (part.counter, whole.counter)):
             dst.copy_(src)
-        part.refresh_alpha()
-        part.prime_alpha()
+        dist.broadcast(part.counter, src=0)
+        broadcast_state(part)  # rank 0's copy everywhere (the ranks' single-process engines differ in the last bits:
+        #                        float atomics), exactly what to_ddp() does before training
         noise = {k: torch.from_numpy(np.asarray(v)) for k, v in g[f"noise{u}"].items()}
         whole.update(u, {k: v.to(dev) for k, v in noise.items()})
         mine = {k: v.to(dev) for k, v in shard(noise, rank, world).items()}
