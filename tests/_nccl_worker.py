@@ -60,15 +60,19 @@ def main():
     broadcast_state(part)
     part.upload_batch(shard(g["batch"], rank, world))
     for u in range(1, m["n_updates"] + 1):
-        # every update starts from the single-process engine's state on all ranks: in the reduced-precision tier the two
-        # trajectories would otherwise drift apart through Adam (|delta w| ~ lr whatever the gradient's size), which
-        # says nothing about the all-reduce
+        # Every update starts, on all ranks and in both engines, from rank 0's single-process state (what to_ddp()'s
+        # broadcast does before training).  Otherwise the ranks' single-process engines differ in the last bits (float
+        # atomics) and, in the reduced-precision tier, trajectories drift apart through Adam (|delta w| ~ lr whatever
+        # the gradient's size) -- neither says anything about the all-reduce.
+        for t in (whole.params, whole.adam_m, whole.adam_v, whole.steps, whole.counter):
+            dist.broadcast(t, src=0)
+        whole.refresh_alpha()
+        whole.prime_alpha()
         for dst, src in ((part.params, whole.params), (part.adam_m, whole.adam_m), (part.adam_v, whole.adam_v),
                          (part.steps, whole.steps), (part.counter, whole.counter)):
             dst.copy_(src)
-        dist.broadcast(part.counter, src=0)
-        broadcast_state(part)  # rank 0's copy everywhere (the ranks' single-process engines differ in the last bits:
-        #                        float atomics), exactly what to_ddp() does before training
+        part.refresh_alpha()
+        part.prime_alpha()
         noise = {k: torch.from_numpy(np.asarray(v)) for k, v in g[f"noise{u}"].items()}
         whole.update(u, {k: v.to(dev) for k, v in noise.items()})
         mine = {k: v.to(dev) for k, v in shard(noise, rank, world).items()}
