@@ -283,6 +283,12 @@ int pcrl_refresh_alpha(const float* log_alpha, float* alpha_dev, float* scalars,
 int pcrl_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, float grad_scale, int32_t* step_dev, float* gradsq_out, float* target,
                    int64_t poly_begin, int64_t poly_end, float tau, void* stream);
+/* One optimizer group updated in several calls (data-parallel runs: the part of the group whose gradient all-reduce has
+ * landed steps while the rest is still in flight).  Exactly one call per update passes bump_step = 1 (it must come first:
+ * the bias corrections read the bumped count) and zero_gradsq = 1; every part adds its share to *gradsq_out. */
+int pcrl_adam_step_part(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                        float eps, float grad_scale, int32_t* step_dev, int bump_step, float* gradsq_out, int zero_gradsq,
+                        float* target, int64_t poly_begin, int64_t poly_end, float tau, void* stream);
 int pcrl_polyak(float* target, const float* source, int64_t n, float tau, void* stream);
 
 #ifdef __cplusplus

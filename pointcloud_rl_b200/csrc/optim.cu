@@ -105,6 +105,24 @@ int pcrl_adam_step(float* p, const float* g, float* m, float* v, int64_t n, floa
   return PCRL_OK;
 }
 
+int pcrl_adam_step_part(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                        float eps, float grad_scale, int32_t* step_dev, int bump_step, float* gradsq_out, int zero_gradsq,
+                        float* target, int64_t poly_begin, int64_t poly_end, float tau, void* stream) {
+  PCRL_CHECK_ARG(p && g && m && v && step_dev && n >= 0);
+  PCRL_CHECK_ARG(!target || (poly_begin % 4 == 0 && poly_begin >= 0 && poly_end <= n && (poly_end % 4 == 0 || poly_end == n)));
+  cudaStream_t st = as_stream(stream);
+  if (bump_step) {
+    bump_step_kernel<<<1, 1, 0, st>>>(step_dev);
+    PCRL_CHECK_LAUNCH();
+  }
+  if (gradsq_out && zero_gradsq) PCRL_CHECK_CUDA(cudaMemsetAsync(gradsq_out, 0, sizeof(float), st));
+  if (n == 0) return PCRL_OK;
+  const int blocks = (int)std::min<int64_t>(cdiv(cdiv(n, 4), 256), (int64_t)sm_count() * 8);
+  adam_kernel<<<std::max(blocks, 1), 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, grad_scale, step_dev,
+                                                   gradsq_out, target, poly_begin, poly_end, tau);
+  PCRL_CHECK_LAUNCH();
+  return PCRL_OK;
+}
 int pcrl_polyak(float* target, const float* source, int64_t n, float tau, void* stream) {
   PCRL_CHECK_ARG(target && source && n >= 0);
   if (n == 0) return PCRL_OK;

@@ -478,7 +478,8 @@ class UpdateEngine:
         self.L.linear_fwd(h1, h1n, p[f"{net}.w1"], p[f"{net}.b1"], h2, h2n, M, h1n, h2n, 1, self.tf32, st)
         self.L.linear_fwd(h2, h2n, p[f"{net}.w2"], p[f"{net}.b2"], out, ldo, M, h2n, nout, 0, self.tf32, st)
 
-    def _mlp_bwd(self, net, x, K, M, dout, lddo, nout, keep, dx, want_w, st, scratch="a", wstream=None, defer=False):
+    def _mlp_bwd(self, net, x, K, M, dout, lddo, nout, keep, dx, want_w, st, scratch="a", wstream=None, defer=False,
+                 join=True):
         """Backward of one 3-layer head.  The data-gradient chain (dX of layer 3 -> 2 -> 1) is the critical path; the
         weight/bias gradients only feed the optimizer, so with `wstream` (three side-stream indices) they run on forked
         streams.  defer=False: each is forked as soon as its dY exists and all are joined before returning.
@@ -528,8 +529,8 @@ class UpdateEngine:
             wgrad(*a)
         if sides is None:
             return []
-        if defer:
-            return sides
+        if defer or not join:
+            return sides  # [layer 0, layer 1, layer 2] weight-gradient streams: the caller joins them
         for side in sides:
             main.wait_stream(side)
         return []
@@ -546,6 +547,21 @@ class UpdateEngine:
                          float(lr), float(betas[0]), float(betas[1]), float(hp.adam_eps), 1.0 / self.world_size,
                          self.steps[idx:], self.scalars[gradsq_slot:] if gradsq_slot is not None else None, target,
                          pb, pe, float(hp.tau), st)
+
+    def _adam_part(self, group, rng, idx, lr, betas, gradsq_slot, first, polyak, st):
+        """Adam over the sub-range `rng` (offsets inside the group) of an optimizer group; `first` = the call that bumps
+        the step count and clears the gradient-norm accumulator.  polyak: the range IS the Q heads (target layout)."""
+        g0 = self.layout.group_range[group][0]
+        lo, hi = g0 + rng[0], g0 + rng[1]
+        hp = self.hp
+        target = None
+        if polyak:
+            t0, t1 = self.layout.group_range["target"]
+            target = self.params[t0:t1]
+        self.L.adam_step_part(self.params[lo:hi], self.grads[lo:hi], self.adam_m[lo:hi], self.adam_v[lo:hi], hi - lo,
+                              float(lr), float(betas[0]), float(betas[1]), float(hp.adam_eps), 1.0 / self.world_size,
+                              self.steps[idx:], int(first), self.scalars[gradsq_slot:], int(first), target, 0,
+                              hi - lo if polyak else 0, float(hp.tau), st)
 
     # ------------------------------------------------------------------ the update
     # ------------------------------------------------------------------ stream forks
@@ -694,10 +710,20 @@ class UpdateEngine:
                        g["pn.w2"], g["pn.g2"], g["pn.be2"], w["scratch"], self.bwd_ws_bytes, self.tf32, w.get("xh_obs"),
                        w.get("wpack"), ST())
         if self.allreduce is not None:
-            self.allreduce(self.grads[c_lo:c_lo + self.layout.q_range[0]])  # PointNet gradients (0.3 MB)
+            # the PointNet gradients (0.3 MB) are reduced on NCCL's stream while Adam already steps the two Q heads,
+            # whose reduction has been in flight since their weight gradients finished; then Adam steps the PointNet
+            s_r = self._side[1]
+            s_r.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s_r):
+                pn_pending = self.allreduce(self.grads[c_lo:c_lo + self.layout.q_range[0]], async_op=True)
             q_pending.wait()
-        self._join(*wg0, *wg1)
-        self._adam("critic", 0, hp.lr, hp.betas, 4, do_target, ST())  # + Polyak fused (sac.py:207-208)
+            self._join(*wg0, *wg1)
+            self._adam_part("critic", self.layout.q_range, 0, hp.lr, hp.betas, 4, True, do_target, ST())
+            pn_pending.wait()
+            self._adam_part("critic", (0, self.layout.q_range[0]), 0, hp.lr, hp.betas, 4, False, False, ST())
+        else:
+            self._join(*wg0, *wg1)
+            self._adam("critic", 0, hp.lr, hp.betas, 4, do_target, ST())  # + Polyak fused (sac.py:207-208)
 
         # ---- actor + alpha step: sac.py:161-205 / drq.py:114-155
         if do_actor:
@@ -734,10 +760,25 @@ class UpdateEngine:
             L.add_cols(da, ld_cat, w["dx1"][:, D + S:], ld_cat, da, ld_cat, B, A, ST())
             L.tanh_gaussian_bwd_dev(w["out_pi"], w["eps_pi"], da, ld_cat, self.alpha_dev, B, A, hp.log_std_bound[0],
                                     hp.log_std_bound[1], hp.head_scale, w["dout"], ST())
-            self._mlp_bwd("actor", cat, D + S, B, w["dout"], 2 * A, 2 * A, "actor", None, True, ST(), "a", wstream=(3, 4, 5))
             if self.allreduce is not None:
-                al_lo, al_hi = self.layout.group_range["alpha"]
-                self.allreduce(self.grads[a_lo:al_hi])  # actor grads | d log_alpha in one message
+                # one all-reduce per layer, issued on NCCL's stream the moment that layer's weight gradient exists
+                # (layer 2 first): only the last bucket -- layer 0, ~1 MB -- is left exposed after the backward
+                wsides = self._mlp_bwd("actor", cat, D + S, B, w["dout"], 2 * A, 2 * A, "actor", None, True, ST(), "a",
+                                       wstream=(3, 4, 5), join=False)
+                al_hi = self.layout.group_range["alpha"][1]
+                ent = self.layout.entries
+                edges = [ent["actor.w0"][0], ent["actor.w1"][0], ent["actor.w2"][0], al_hi]  # (w, b) pairs; alpha rides with layer 2
+                s_r = self._side[1]
+                pend = []
+                for layer in (2, 1, 0):
+                    s_r.wait_stream(wsides[layer])
+                    with torch.cuda.stream(s_r):
+                        pend.append(self.allreduce(self.grads[edges[layer]:edges[layer + 1]], async_op=True))
+                for h in pend:
+                    h.wait()
+                self._join(*wsides)
+            else:
+                self._mlp_bwd("actor", cat, D + S, B, w["dout"], 2 * A, 2 * A, "actor", None, True, ST(), "a", wstream=(3, 4, 5))
             self._adam("actor", 1, hp.actor_lr, hp.actor_betas, 8, False, ST())
             if hp.automatic_alpha_tuning:
                 self._adam("alpha", 2, hp.alpha_lr, hp.alpha_betas, None, False, ST())
