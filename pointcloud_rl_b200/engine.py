@@ -328,7 +328,11 @@ class UpdateEngine:
             self._pinned_i = 0
             from concurrent.futures import ThreadPoolExecutor
 
-            self._copy_pool = ThreadPoolExecutor(max_workers=4, thread_name_prefix="pcrl-stage")
+            # staging threads: up to 4, but never more than this rank's share of the host cores (8 ranks on a 16-core
+            # box get one each: oversubscribed memcpy threads slow every rank's host path down)
+            ranks_here = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
+            n_thr = max(1, min(4, (os.cpu_count() or 4) // max(1, ranks_here) - 1))
+            self._copy_pool = ThreadPoolExecutor(max_workers=n_thr, thread_name_prefix="pcrl-stage")
         i = self._pinned_i = self._pinned_i ^ 1
         if self._pinned_ev[i] is not None:
             self._pinned_ev[i].synchronize()
