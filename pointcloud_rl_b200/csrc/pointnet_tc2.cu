@@ -346,8 +346,7 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t taddr = tmem_base + (uint32_t)(s * 128) + ((uint32_t)(q * 32) << 16);
-    const float* g1 = reinterpret_cast<const float*>(smem + L.img + W.prm1);
-    const float* be1 = g1 + C2;
+    const float* be1 = reinterpret_cast<const float*>(smem + L.img + W.prm1);  // beta1 / |gamma1|
     unsigned char* abuf = smem + L.act + (uint32_t)s * kActBytes;
     unsigned char* dst0 = abuf + (row >> 3) * (uint32_t)(C1 * 16) + (row & 7) * 16;
     unsigned char* dst1 = abuf + (row >> 3) * (uint32_t)(C2 * 16) + (row & 7) * 16;
@@ -413,12 +412,12 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
             hp[(ch + j4) / 2 + 1] = v[j4 + 2];
             continue;
           }
-          const float4 gg = *reinterpret_cast<const float4*>(g1 + ch + j4);
+          // gamma1 is folded away by the packer (sign into W1c's rows, |gamma1| into W2c's columns and the Gram matrix):
+          // h1' = relu(xhat' + beta1 / |gamma1|) -- one FMA and one broadcast shared-memory load per 4 channels less
           const float4 bb = *reinterpret_cast<const float4*>(be1 + ch + j4);
-          const uint64_t zero2 = pk2f(0.f, 0.f);
           uint32_t x0, x1, x2, x3;
-          unpk2(fma2(fma2(pk2(v[j4], v[j4 + 1]), r2, zero2), pk2f(gg.x, gg.y), pk2f(bb.x, bb.y)), x0, x1);
-          unpk2(fma2(fma2(pk2(v[j4 + 2], v[j4 + 3]), r2, zero2), pk2f(gg.z, gg.w), pk2f(bb.z, bb.w)), x2, x3);
+          unpk2(fma2(pk2(v[j4], v[j4 + 1]), r2, pk2f(bb.x, bb.y)), x0, x1);
+          unpk2(fma2(pk2(v[j4 + 2], v[j4 + 3]), r2, pk2f(bb.z, bb.w)), x2, x3);
           hp[(ch + j4) / 2] = pack_relu_bf16x2(__uint_as_float(x0), __uint_as_float(x1));
           hp[(ch + j4) / 2 + 1] = pack_relu_bf16x2(__uint_as_float(x2), __uint_as_float(x3));
         }
@@ -499,6 +498,80 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
       tr(1000 * j + 400);
       const float* rb = rbuf + (j & 3) * 128;
       const uint32_t idx_base = (uint32_t)((int)(tile % tiles_per_cloud) * 128);
+      if (NBLK == 2) {
+        // Both 128-channel blocks of the tile together, 32 points at a time: the per-point rstd2 (a broadcast
+        // shared-memory load -- a full wavefront per point and warp, and the shared-memory pipe is what this kernel
+        // runs out of) is loaded ONCE for the two blocks.
+        mbar_wait(BAR(F2 + 0), j & 1);
+        mbar_wait(BAR(F2 + 1), j & 1);
+        tr(1000 * j + 410);
+        tc_fence_after();
+        const uint32_t ta = tmem_base + 256u + lane_off, tb = ta + 128u;
+        uint32_t ka0 = 0, ka1 = 0, kb0 = 0, kb1 = 0;
+        float ma0 = m[0], ma1 = -3.0e38f, mb0 = m[NBLK - 1], mb1 = -3.0e38f;
+        uint32_t va[32], vb[32];
+#pragma unroll
+        for (int ch = 0; ch < 128; ch += 32) {
+          if (!(dbg & 16)) {
+            tmem_ld32_async(ta + ch, va);
+            tmem_ld32_async(tb + ch, vb);
+            tmem_wait_ld_dep(va);
+            tmem_wait_ld_dep(vb);
+          }
+          if (ch == 96) {  // every column of both blocks has been read: hand the ring slots back before the last chunk's math
+            tc_fence_before();
+            mbar_arrive(BAR(D2 + 0));
+            mbar_arrive(BAR(D2 + 1));
+          }
+          if (dbg & 1) continue;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 rr = *reinterpret_cast<const float4*>(rb + ch + i);  // broadcast
+            const uint64_t r01 = pk2f(rr.x, rr.y), r23 = pk2f(rr.z, rr.w);
+            if (ARGMAX) {
+              uint32_t z0, z1, z2, z3;
+              unpk2(fma2(pk2(va[i], va[i + 1]), r01, bias2), z0, z1);
+              unpk2(fma2(pk2(va[i + 2], va[i + 3]), r23, bias2), z2, z3);
+              z0 = (z0 & 0xffffff80u) | (uint32_t)(127 - (ch + i));
+              z1 = (z1 & 0xffffff80u) | (uint32_t)(127 - (ch + i + 1));
+              z2 = (z2 & 0xffffff80u) | (uint32_t)(127 - (ch + i + 2));
+              z3 = (z3 & 0xffffff80u) | (uint32_t)(127 - (ch + i + 3));
+              ka0 = __vimax3_u32(ka0, z0, z1);
+              ka1 = __vimax3_u32(ka1, z2, z3);
+              unpk2(fma2(pk2(vb[i], vb[i + 1]), r01, bias2), z0, z1);
+              unpk2(fma2(pk2(vb[i + 2], vb[i + 3]), r23, bias2), z2, z3);
+              z0 = (z0 & 0xffffff80u) | (uint32_t)(127 - (ch + i));
+              z1 = (z1 & 0xffffff80u) | (uint32_t)(127 - (ch + i + 1));
+              z2 = (z2 & 0xffffff80u) | (uint32_t)(127 - (ch + i + 2));
+              z3 = (z3 & 0xffffff80u) | (uint32_t)(127 - (ch + i + 3));
+              kb0 = __vimax3_u32(kb0, z0, z1);
+              kb1 = __vimax3_u32(kb1, z2, z3);
+            } else {
+              const uint64_t zero2 = pk2f(0.f, 0.f);
+              uint32_t z0, z1, z2, z3;
+              unpk2(fma2(pk2(va[i], va[i + 1]), r01, zero2), z0, z1);
+              unpk2(fma2(pk2(va[i + 2], va[i + 3]), r23, zero2), z2, z3);
+              ma0 = fmax3(ma0, __uint_as_float(z0), __uint_as_float(z1));
+              ma1 = fmax3(ma1, __uint_as_float(z2), __uint_as_float(z3));
+              unpk2(fma2(pk2(vb[i], vb[i + 1]), r01, zero2), z0, z1);
+              unpk2(fma2(pk2(vb[i + 2], vb[i + 3]), r23, zero2), z2, z3);
+              mb0 = fmax3(mb0, __uint_as_float(z0), __uint_as_float(z1));
+              mb1 = fmax3(mb1, __uint_as_float(z2), __uint_as_float(z3));
+            }
+          }
+        }
+        if (ARGMAX) {
+          const uint32_t ka = max(ka0, ka1), kb = max(kb0, kb1);
+          const uint32_t ia = idx_base + (127u - (ka & 127u)), ib = idx_base + (127u - (kb & 127u));
+          run[0] = max(run[0], ((unsigned long long)(ka & 0xffffff80u) << 32) | (unsigned long long)(0xFFFFFFFFu - ia));
+          run[NBLK - 1] = max(run[NBLK - 1], ((unsigned long long)(kb & 0xffffff80u) << 32) | (unsigned long long)(0xFFFFFFFFu - ib));
+        } else {
+          m[0] = fmaxf(ma0, ma1);
+          m[NBLK - 1] = fmaxf(mb0, mb1);
+        }
+        tr(1000 * j + 421);
+        continue;
+      }
 #pragma unroll
       for (int blk = 0; blk < NBLK; ++blk) {
         const int g = j * NBLK + blk, r = g & 1, k = g >> 1;
@@ -578,6 +651,9 @@ __device__ __forceinline__ uint32_t img_off(int n, int k, int K) {
   return (uint32_t)((n >> 3) * (K * 16) + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2);
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
+// relu(g x + b) = |g| relu(sign(g) x + b / |g|): |gamma1| moves into the next layer's weights.  A gain of exactly zero
+// (relu(b), independent of x) is treated as 1e-12: x's contribution vanishes below fp32 resolution all the same.
+__device__ __forceinline__ float gamma1_mag(float g) { return fmaxf(fabsf(g), 1e-12f); }
 
 // Column means of W1 (over its c2 rows) and W2 (over its c3 rows): block 0 / block 1, 1024 threads = 8 row groups x
 // (up to) 128 columns, reduced through shared memory.  ~1.5 us; the packer reads the result.
@@ -623,16 +699,19 @@ pack_weights2_kernel(const float* __restrict__ w0, const float* __restrict__ b0,
     }
     *reinterpret_cast<__nv_bfloat16*>(out + W.w0 + img_off(n, k, 16)) = __float2bfloat16(v);
   } else if (i < n0 + n1) {
+    // layer 1: centred over the output channels, sign(gamma1) folded into the rows (the variance is unchanged)
     const int e = i - n0, n = e / c1, k = e % c1;
-    *reinterpret_cast<__nv_bfloat16*>(out + W.w1 + img_off(n, k, c1)) = __float2bfloat16(w1[e] - m1[k]);
+    const float v = w1[e] - m1[k];
+    *reinterpret_cast<__nv_bfloat16*>(out + W.w1 + img_off(n, k, c1)) = __float2bfloat16(g1[n] >= 0.f ? v : -v);
   } else if (i < n0 + n1 + n2) {
+    // layer 2: centred over the output channels, sign(gamma2) folded into the rows, |gamma1| into the columns
     const int e = i - n0 - n1, n = e / c2, k = e % c2;
-    const float v = w2[e] - m2[k];
+    const float v = (w2[e] - m2[k]) * gamma1_mag(g1[k]);
     *reinterpret_cast<__nv_bfloat16*>(out + W.w2 + img_off(n, k, c2)) = __float2bfloat16(g2[n] >= 0.f ? v : -v);
   } else if (i >= n0 + n1 + n2 + n3 && i < n0 + n1 + n2 + n3 + n4) {
     const int e = i - n0 - n1 - n2 - n3;
-    if (e < c2) reinterpret_cast<float*>(out + W.prm1)[e] = g1[e];
-    else if (e < 2 * c2) reinterpret_cast<float*>(out + W.prm1)[e] = be1[e - c2];
+    if (e < c2) reinterpret_cast<float*>(out + W.prm1)[e] = be1[e] / gamma1_mag(g1[e]);  // beta1 / |gamma1|
+    else if (e < 2 * c2) reinterpret_cast<float*>(out + W.prm1)[e] = 0.f;
     else if (e < 2 * c2 + c3) reinterpret_cast<float*>(out + W.prm2)[e - 2 * c2] = g2[e - 2 * c2];
     else reinterpret_cast<float*>(out + W.prm2)[e - 2 * c2] = be2[e - 2 * c2 - c3];
   }
@@ -643,15 +722,17 @@ pack_weights2_kernel(const float* __restrict__ w0, const float* __restrict__ b0,
 // loads coalesce, the k column is a broadcast) and the partials meet in shared memory.  ~2 us, where one thread per
 // output looping over all c3 rows is latency-bound at ~20 us.
 __global__ void __launch_bounds__(256)
-gram_kernel(const float* __restrict__ w2, const float* __restrict__ m2, int c2, int c3, char* __restrict__ gc_img) {
+gram_kernel(const float* __restrict__ w2, const float* __restrict__ m2, const float* __restrict__ g1, int c2, int c3,
+            char* __restrict__ gc_img) {
   __shared__ float part[8][33];
   const int o = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int e = blockIdx.x * 32 + o, k = e / c2, kk = e % c2;
-  const float mk = m2[k], mkk = m2[kk];
+  const float mk = m2[k], mkk = m2[kk], ak = gamma1_mag(g1[k]), akk = gamma1_mag(g1[kk]);
   float s0 = 0.f, s1 = 0.f;
   for (int n = g; n < c3; n += 16) {
-    s0 = fmaf(bf16_round(w2[n * c2 + k] - mk), bf16_round(w2[n * c2 + kk] - mkk), s0);
-    if (n + 8 < c3) s1 = fmaf(bf16_round(w2[(n + 8) * c2 + k] - mk), bf16_round(w2[(n + 8) * c2 + kk] - mkk), s1);
+    s0 = fmaf(bf16_round((w2[n * c2 + k] - mk) * ak), bf16_round((w2[n * c2 + kk] - mkk) * akk), s0);
+    if (n + 8 < c3)
+      s1 = fmaf(bf16_round((w2[(n + 8) * c2 + k] - mk) * ak), bf16_round((w2[(n + 8) * c2 + kk] - mkk) * akk), s1);
   }
   part[g][o] = s0 + s1;
   __syncthreads();
@@ -680,8 +761,8 @@ int pack(const float* w0, const float* b0, const float* w1, const float* g1, con
                                                                 (char*)wpack2);
   PCRL_CHECK_LAUNCH();
   const Wpack2 W = make_wpack2(c1, c2, c3);
-  gram_kernel<<<(unsigned)(c2 * c2 / 32), 256, 0, st>>>(w2, reinterpret_cast<const float*>((char*)wpack2 + W.cm) + c1, c2, c3,
-                                                       (char*)wpack2 + W.gc);
+  gram_kernel<<<(unsigned)(c2 * c2 / 32), 256, 0, st>>>(w2, reinterpret_cast<const float*>((char*)wpack2 + W.cm) + c1, g1, c2,
+                                                       c3, (char*)wpack2 + W.gc);
   PCRL_CHECK_LAUNCH();
   return PCRL_OK;
 }
