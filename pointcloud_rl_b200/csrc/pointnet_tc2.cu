@@ -190,13 +190,19 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
   constexpr int F2 = HF + 2;        // [ring] transposed layer-2 accumulator complete
   constexpr int D2 = F2 + 2;        // [ring] ... drained by the pool group (128 arrivals)
   constexpr int UI = D2 + 2;        // [slot] the Gram MMA has been ISSUED (the transposed layer 2 queues behind it)
-  constexpr int NBAR = UI + 2;
+  constexpr int W1B = UI + 2;       // W1c + beta1' landed   } the weight image arrives in four pieces so that the first
+  constexpr int WGB = W1B + 1;      // Gc landed             } tiles' layer 0 / 1 run while the 96 KB of Gc and W2c'
+  constexpr int W2B = WGB + 1;      // W2c' slice landed     } are still on their way (WB: W0' only)
+  constexpr int NBAR = W2B + 1;
   const uint32_t bar0 = sbase + L.bars;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L.bars + NBAR * 8);
 
   if (threadIdx.x == 0) {
     mbar_init(BAR(WB), 1);
+    mbar_init(BAR(W1B), 1);
+    mbar_init(BAR(WGB), 1);
+    mbar_init(BAR(W2B), 1);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(BAR(XF + s), 1);
       mbar_init(BAR(XE + s), 1);
@@ -242,16 +248,30 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_expect_tx(BAR(WB), W.img_bytes);
-      // [W0' | W1c | Gc] is contiguous in both images; then this group's slice of W2c'; then g1 | be1
-      for (uint32_t off = 0; off < W.w2; off += 32768u)
-        bulk_g2s(sbase + L.img + off, wpack + off, min(W.w2 - off, 32768u), BAR(WB));
+      // [W0' | W1c | Gc] is contiguous in both images; then this group's slice of W2c'; then beta1'
+      auto load = [&](uint32_t dst_off, uint32_t src_off, uint32_t bytes, int bar) {
+        mbar_expect_tx(BAR(bar), bytes);
+        for (uint32_t off = 0; off < bytes; off += 32768u)
+          bulk_g2s(sbase + L.img + dst_off + off, wpack + src_off + off, min(bytes - off, 32768u), BAR(bar));
+      };
       const uint32_t w2_bytes = W.prm1 - W.w2;
-      for (uint32_t off = 0; off < w2_bytes; off += 32768u)
-        bulk_g2s(sbase + L.img + W.w2 + off, wpack + WG.w2 + (uint32_t)group * w2_bytes + off, min(w2_bytes - off, 32768u),
-                 BAR(WB));
-      bulk_g2s(sbase + L.img + W.prm1, wpack + WG.prm1, W.img_bytes - W.prm1, BAR(WB));
-      for (int i = 0; i < n_local; ++i) {
+      load(W.w0, WG.w0, W.w1 - W.w0, WB);
+      mbar_expect_tx(BAR(W1B), (W.gc - W.w1) + (W.img_bytes - W.prm1));
+      for (uint32_t off = 0; off < W.gc - W.w1; off += 32768u)
+        bulk_g2s(sbase + L.img + W.w1 + off, wpack + WG.w1 + off, min(W.gc - W.w1 - off, 32768u), BAR(W1B));
+      bulk_g2s(sbase + L.img + W.prm1, wpack + WG.prm1, W.img_bytes - W.prm1, BAR(W1B));
+      // the first point tiles go out before the big weight pieces
+      const int n_first = min(n_local, kStages);
+      for (int i = 0; i < n_first; ++i) {
+        mbar_expect_tx(BAR(XF + i), kTileBytes);
+        const int64_t tile = tile0 + i;
+        const int64_t src_tile = src_cloud_stride == 1 ? tile
+                                                        : (tile / tiles_per_cloud) * src_cloud_stride * tiles_per_cloud + tile % tiles_per_cloud;
+        bulk_g2s(sbase + L.xst + i * kTileBytes, xh + src_tile * kTileBytes, kTileBytes, BAR(XF + i));
+      }
+      load(W.gc, WG.gc, W.w2 - W.gc, WGB);
+      load(W.w2, WG.w2 + (uint32_t)group * w2_bytes, w2_bytes, W2B);
+      for (int i = n_first; i < n_local; ++i) {
         const int st = i % kStages;
         if (i >= kStages) mbar_wait_relaxed(BAR(XE + st), ((i / kStages) - 1) & 1, 64);
         mbar_expect_tx(BAR(XF + st), kTileBytes);
@@ -290,6 +310,7 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
       }
       __syncwarp();
       mbar_wait(BAR(E0 + s), n & 1);  // h0 in shared memory, acc0 drained
+      if (n == 0) mbar_wait(BAR(W1B), 0);
       tr(1000 * j + 110);
       tc_fence_after();
       if (elect_one()) {
@@ -299,6 +320,7 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
       }
       __syncwarp();
       mbar_wait(BAR(E1 + s), n & 1);  // h1 in shared memory, acc1 drained
+      if (n == 0) mbar_wait(BAR(WGB), 0);
       tr(1000 * j + 120);
       tc_fence_after();
       if (elect_one()) {
@@ -315,7 +337,7 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
     const uint32_t idT = make_idesc(128);  // N = the tile's 128 points
     const uint64_t d_w2 = make_desc(s_w2, C2 * 16);
     const uint64_t d_a0 = make_desc(sbase + L.act, C2 * 16), d_a1 = make_desc(sbase + L.act + kActBytes, C2 * 16);
-    mbar_wait(BAR(WB), 0);
+    mbar_wait(BAR(W2B), 0);
     Tracer2 tr{2, 0, (dbg & 256) && blockIdx.x == 0 && lane == 0};
     for (int j = 0; j < n_local; ++j) {
       const int s = j & 1, n = j >> 1;
@@ -353,7 +375,7 @@ pointnet_fwd_tc2_kernel(const char* __restrict__ xh, const char* __restrict__ wp
     float* rbuf = reinterpret_cast<float*>(smem + L.rbuf);
     const float inv_c3 = 1.0f / (float)c3_total;
     const bool no_ld = dbg & 8;
-    mbar_wait(BAR(WB), 0);  // LN parameters landed
+    mbar_wait(BAR(W1B), 0);  // LN parameters landed
     Tracer2 tr{3 + s, 0, (dbg & 256) && blockIdx.x == 0 && lane == 0 && q == 0};
     for (int j = s; j < n_local; j += 2) {
       const int n = j >> 1;
