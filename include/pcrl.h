@@ -100,6 +100,11 @@ int pcrl_downsample_map(int N, float drop_ratio, int fixed_ratio, uint64_t seed,
 int pcrl_gather_transitions(const uint64_t* src_ptrs, const uint64_t* dst_ptrs, const int64_t* row_bytes, int n_leaves,
                             const int64_t* idx, int B, void* stream);
 
+/* Host-side helper of the batch upload (GDict.to_torch, dict_array.py:308-318): memcpy between two HOST buffers on
+ * `threads` threads of a small persistent pool (caller included).  Used to stage the pageable arrays `memory.sample`
+ * returns into the pinned buffer the H2D copy reads; both pointers are host pointers. */
+int pcrl_host_memcpy_mt(void* dst_host, const void* src_host, int64_t nbytes, int threads);
+
 /* ColorJitterPoints (pyrl/utils/augmentations/pcd_aug.py:269-303 -> torchvision ColorJitter on [B',3,1,N] uint8):
  * rgb u8 [B,3,N] -> out u8 [B,3,N].  One parameter set per CALL is shared by all clouds (so the num_aug copies of a
  * sample are identical: run it on the B source clouds and let pcrl_stage_points repeat them).

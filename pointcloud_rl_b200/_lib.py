@@ -72,7 +72,8 @@ class _Lib:
             raise AttributeError(name)
         fn = getattr(self.cdll, full)
         restype, args = protos[full]
-        is_status = restype is ctypes.c_int and name not in ("abi_version", "sm_count", "set_strict_tf32", "destroy")
+        is_status = restype is ctypes.c_int and name not in ("abi_version", "sm_count", "set_strict_tf32", "destroy",
+                                                             "host_memcpy_mt")
 
         def call(*a):
             conv = []

@@ -318,44 +318,35 @@ class UpdateEngine:
     def upload_batch(self, batch):
         """batch: dict(obs, next_obs, actions, rewards, dones) of numpy arrays / torch CPU tensors (the
         reference's `memory.sample(B)` layout, replay_buffer.py:297-322).  Every leaf is copied into its slot of ONE
-        pinned staging buffer and its host->device copy is enqueued at once, so the DMA of leaf i overlaps the host
-        memcpy of leaf i+1; two staging buffers alternate so a call never overwrites bytes a previous call's DMA
-        may still be reading."""
+        pinned staging buffer (multi-threaded memcpy inside the library) and its host->device copy is enqueued at once, so
+        the DMA of leaf i overlaps the host memcpy of leaf i+1; two staging buffers alternate so a call never overwrites
+        bytes a previous call's DMA may still be reading."""
         if self._pinned is None:
             self._pinned = [torch.empty(self._batch_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
             self._pinned_np = [{k: v.numpy() for k, v in self._batch_views(p).items()} for p in self._pinned]
             self._pinned_ev = [None, None]
             self._pinned_i = 0
-            from concurrent.futures import ThreadPoolExecutor
-
             # staging threads: up to 4, but never more than this rank's share of the host cores (8 ranks on a 16-core
             # box get one each: oversubscribed memcpy threads slow every rank's host path down)
             ranks_here = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
-            n_thr = max(1, min(4, (os.cpu_count() or 4) // max(1, ranks_here) - 1))
-            self._copy_pool = ThreadPoolExecutor(max_workers=n_thr, thread_name_prefix="pcrl-stage")
+            self._copy_threads = max(1, min(4, (os.cpu_count() or 4) // max(1, ranks_here) - 1))
         i = self._pinned_i = self._pinned_i ^ 1
         if self._pinned_ev[i] is not None:
             self._pinned_ev[i].synchronize()
         host, views = self._pinned[i], self._pinned_np[i]
-        # host memcpy of the big leaves in row chunks on a few threads (numpy releases the GIL while it copies); the
-        # H2D copy of a chunk is enqueued as soon as its bytes are staged, so PCIe runs under the remaining memcpys
-        jobs = []
-        for key, _shape, _dt, off, nbytes in self._batch_layout:
-            src = self._host_leaf(batch, key)
-            dst = views[key]
-            src = src.reshape(dst.shape)
-            rows = dst.shape[0]
-            n_chunks = min(rows, max(1, nbytes // (1 << 20)))
-            step = -(-rows // n_chunks)
-            row_bytes = nbytes // rows
-            for r0 in range(0, rows, step):
-                r1 = min(rows, r0 + step)
-                fut = self._copy_pool.submit(np.copyto, dst[r0:r1], src[r0:r1], "unsafe")  # bool -> u8, f64 -> f32
-                jobs.append((fut, off + r0 * row_bytes, off + r1 * row_bytes))
+        base = host.data_ptr()
         with torch.cuda.device(self.device):
-            for fut, b0, b1 in jobs:
-                fut.result()
-                self.raw_flat[b0:b1].copy_(host[b0:b1], non_blocking=True)
+            for key, _shape, _dt, off, nbytes in self._batch_layout:
+                src = self._host_leaf(batch, key)
+                dst = views[key]
+                if src.flags.c_contiguous and src.dtype.itemsize == dst.dtype.itemsize and src.nbytes == nbytes and (
+                        src.dtype == dst.dtype or src.dtype == np.bool_):
+                    # same bytes (float32 -> float32, uint8 / bool -> uint8): the library's multi-threaded memcpy
+                    self.L.host_memcpy_mt(base + off, src.ctypes.data, nbytes, self._copy_threads)
+                else:
+                    np.copyto(dst, src.reshape(dst.shape), casting="unsafe")  # f64 -> f32, strided sources, ...
+                # the DMA of this leaf runs under the memcpy of the next one
+                self.raw_flat[off:off + nbytes].copy_(host[off:off + nbytes], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
             self._pinned_ev[i] = ev
