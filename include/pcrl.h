@@ -105,6 +105,14 @@ int pcrl_gather_transitions(const uint64_t* src_ptrs, const uint64_t* dst_ptrs, 
  * returns into the pinned buffer the H2D copy reads; both pointers are host pointers. */
 int pcrl_host_memcpy_mt(void* dst_host, const void* src_host, int64_t nbytes, int threads);
 
+/* The whole batch upload in one call (GDict.to_torch(device=...), dict_array.py:308-318, for every leaf of
+ * `memory.sample(B)`): leaf i = sizes[i] bytes from HOST pointer srcs_host[i] (NULL: the caller already wrote it) is
+ * staged at pinned_host + offsets[i] with the pool memcpy above, and its host->device copy to landing_dev + offsets[i]
+ * is enqueued on `stream` immediately, so the DMA of a leaf overlaps the staging of the next one.  pinned_host must be
+ * page-locked; srcs_host / offsets / sizes are HOST arrays of n_leaves entries. */
+int pcrl_upload_leaves(void* pinned_host, void* landing_dev, const void* const* srcs_host, const int64_t* offsets,
+                       const int64_t* sizes, int n_leaves, int threads, void* stream);
+
 /* ColorJitterPoints (pyrl/utils/augmentations/pcd_aug.py:269-303 -> torchvision ColorJitter on [B',3,1,N] uint8):
  * rgb u8 [B,3,N] -> out u8 [B,3,N].  One parameter set per CALL is shared by all clouds (so the num_aug copies of a
  * sample are identical: run it on the B source clouds and let pcrl_stage_points repeat them).

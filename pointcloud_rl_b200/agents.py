@@ -379,10 +379,23 @@ class SAC(BaseAgent):
             eng.update_graphed(updates)
         else:
             eng.update(updates)
-        ret = eng.read_scalars(updates)
-        self.alpha = eng._alpha_before
+        # the scalars come back asynchronously (engine.LazyScalars: a dict that waits for its device->host copy on first
+        # access), so the next call can sample and stage its batch while this update is still running
+        ret = eng.read_scalars_async(updates)
         self._weights_changed()
         return ret
+
+    @property
+    def alpha(self):
+        """exp(log_alpha) as last cached by an update (sac.py:152); waits for updates still in flight."""
+        if self.engine is not None:
+            self.engine.flush_scalars()
+            return self.engine._alpha_before
+        return self._alpha
+
+    @alpha.setter
+    def alpha(self, v):
+        self._alpha = v
 
     def _weights_changed(self):
         """The rollout path caches the packed MMA images of the PointNet weights: tell it they moved."""

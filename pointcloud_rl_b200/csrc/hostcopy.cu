@@ -102,3 +102,21 @@ extern "C" int pcrl_host_memcpy_mt(void* dst_host, const void* src_host, int64_t
   pcrl::pool().copy(dst_host, src_host, nbytes, threads);
   return PCRL_OK;
 }
+
+// One call per replay batch: every leaf is staged into its slot of the pinned buffer (pool memcpy; leaves with a NULL
+// source were already written there by the caller) and its host->device copy is enqueued on `stream` right away, so the
+// DMA of leaf i runs under the memcpy of leaf i+1 and the python side pays one foreign call instead of ~5 per leaf.
+extern "C" int pcrl_upload_leaves(void* pinned_host, void* landing_dev, const void* const* srcs_host,
+                                  const int64_t* offsets, const int64_t* sizes, int n_leaves, int threads, void* stream) {
+  PCRL_CHECK_ARG(n_leaves >= 0 && (n_leaves == 0 || (pinned_host && landing_dev && srcs_host && offsets && sizes)));
+  cudaStream_t st = pcrl::as_stream(stream);
+  for (int i = 0; i < n_leaves; ++i) {
+    PCRL_CHECK_ARG(offsets[i] >= 0 && sizes[i] >= 0);
+    if (sizes[i] == 0) continue;
+    char* h = static_cast<char*>(pinned_host) + offsets[i];
+    if (srcs_host[i]) pcrl::pool().copy(h, srcs_host[i], sizes[i], threads);
+    PCRL_CHECK_CUDA(cudaMemcpyAsync(static_cast<char*>(landing_dev) + offsets[i], h, (size_t)sizes[i],
+                                    cudaMemcpyHostToDevice, st));
+  }
+  return PCRL_OK;
+}

@@ -17,6 +17,7 @@ import torch
 
 from ._lib import lib, stream_ptr
 
+import ctypes
 import os
 
 _NO_FORK = os.environ.get("PCRL_NO_FORK", "")
@@ -32,6 +33,61 @@ PN_KEYS = ["pn.w0", "pn.b0", "pn.w1", "pn.g1", "pn.be1", "pn.w2", "pn.g2", "pn.b
 
 def _align(n, a):
     return (n + a - 1) // a * a
+
+
+SCALAR_RING = 8  # asynchronous scalar results in flight (pinned slots)
+
+
+class LazyScalars(dict):
+    """The dict `update_parameters` returns (sac.py:140-203: name -> python float), filled in on first access.  The
+    values were copied device->host behind the update; touching the dict (indexing, iteration, len, repr, ...) waits for
+    that copy.  A caller that reads it right away sees exactly the synchronous behaviour; a training loop that logs the
+    previous update's scalars after launching the next one never blocks on the GPU."""
+
+    __slots__ = ("_engine", "_slot", "_event", "_updates")
+
+    def __init__(self, engine, slot, event, updates):
+        super().__init__()
+        self._engine, self._slot, self._event, self._updates = engine, slot, event, updates
+
+    def _resolve(self):
+        eng = self._engine
+        if eng is None:
+            return
+        pending = eng._scalar_pending
+        while pending and pending[0] is not self:  # earlier updates first (alpha is carried from one to the next)
+            pending[0]._resolve()
+        self._event.synchronize()
+        s = self._slot.numpy().astype(np.float64)
+        self._engine = None
+        if pending and pending[0] is self:
+            pending.pop(0)
+        dict.update(self, eng._scalars_dict(s, self._updates))
+
+    @property
+    def ready(self):
+        """True once the values are on the host (never blocks)."""
+        return self._engine is None or (self._engine._scalar_pending[0] is self and self._event.query())
+
+
+def _resolving(name):
+    base = getattr(dict, name)
+
+    def method(self, *a, **k):
+        self._resolve()
+        return base(self, *a, **k)
+
+    method.__name__ = name
+    return method
+
+
+for _n in ("__getitem__", "__iter__", "__len__", "__contains__", "__repr__", "__eq__", "__ne__", "__reversed__", "__or__",
+           "__ror__", "__setitem__", "__delitem__", "get", "items", "keys", "values", "copy", "pop", "popitem", "setdefault",
+           "update", "__str__", "__bool__"):
+    if hasattr(dict, _n):
+        setattr(LazyScalars, _n, _resolving(_n))
+LazyScalars.__bool__ = lambda self: len(self) > 0
+LazyScalars.__reduce__ = lambda self: (dict, (dict(self.items()),))
 
 
 @dataclass
@@ -318,14 +374,23 @@ class UpdateEngine:
     def upload_batch(self, batch):
         """batch: dict(obs, next_obs, actions, rewards, dones) of numpy arrays / torch CPU tensors (the
         reference's `memory.sample(B)` layout, replay_buffer.py:297-322).  Every leaf is copied into its slot of ONE
-        pinned staging buffer (multi-threaded memcpy inside the library) and its host->device copy is enqueued at once, so
-        the DMA of leaf i overlaps the host memcpy of leaf i+1; two staging buffers alternate so a call never overwrites
-        bytes a previous call's DMA may still be reading."""
+        pinned staging buffer (multi-threaded memcpy inside the library) and its host->device copy is enqueued at once
+        on a COPY stream into a landing buffer in HBM, so the DMA of leaf i overlaps the host memcpy of leaf i+1 and the
+        whole transfer overlaps the previous update still running on the compute stream; the compute stream then waits
+        for the DMA and adopts the landing buffer with one device-to-device copy (10 MB, ~7 us).  Pinned and landing
+        buffers alternate (two each) so a call never overwrites bytes an earlier copy may still be reading."""
         if self._pinned is None:
             self._pinned = [torch.empty(self._batch_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
             self._pinned_np = [{k: v.numpy() for k, v in self._batch_views(p).items()} for p in self._pinned]
             self._pinned_ev = [None, None]
             self._pinned_i = 0
+            self._landing = [torch.empty_like(self.raw_flat) for _ in range(2)]
+            self._landing_free = [None, None]
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            n = len(self._batch_layout)
+            self._leaf_srcs = (ctypes.c_void_p * n)()
+            self._leaf_offs = (ctypes.c_int64 * n)(*[off for *_, off, _nb in self._batch_layout])
+            self._leaf_sizes = (ctypes.c_int64 * n)(*[nb for *_, nb in self._batch_layout])
             # staging threads: up to 4, but never more than this rank's share of the host cores (8 ranks on a 16-core
             # box get one each: oversubscribed memcpy threads slow every rank's host path down)
             ranks_here = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
@@ -333,23 +398,37 @@ class UpdateEngine:
         i = self._pinned_i = self._pinned_i ^ 1
         if self._pinned_ev[i] is not None:
             self._pinned_ev[i].synchronize()
-        host, views = self._pinned[i], self._pinned_np[i]
+        host, views, land = self._pinned[i], self._pinned_np[i], self._landing[i]
         base = host.data_ptr()
         with torch.cuda.device(self.device):
-            for key, _shape, _dt, off, nbytes in self._batch_layout:
+            cs, main = self._copy_stream, torch.cuda.current_stream()
+            if self._landing_free[i] is not None:
+                cs.wait_event(self._landing_free[i])  # the adopt copy that last read this landing buffer
+            keep = []  # source arrays stay referenced until the call returns
+            for j, (key, _shape, _dt, off, nbytes) in enumerate(self._batch_layout):
                 src = self._host_leaf(batch, key)
                 dst = views[key]
                 if src.flags.c_contiguous and src.dtype.itemsize == dst.dtype.itemsize and src.nbytes == nbytes and (
                         src.dtype == dst.dtype or src.dtype == np.bool_):
                     # same bytes (float32 -> float32, uint8 / bool -> uint8): the library's multi-threaded memcpy
-                    self.L.host_memcpy_mt(base + off, src.ctypes.data, nbytes, self._copy_threads)
+                    keep.append(src)
+                    self._leaf_srcs[j] = src.ctypes.data
                 else:
                     np.copyto(dst, src.reshape(dst.shape), casting="unsafe")  # f64 -> f32, strided sources, ...
-                # the DMA of this leaf runs under the memcpy of the next one
-                self.raw_flat[off:off + nbytes].copy_(host[off:off + nbytes], non_blocking=True)
+                    self._leaf_srcs[j] = None
+            # one foreign call: stage every leaf into the pinned buffer and enqueue its DMA on the copy stream at once
+            self.L.upload_leaves(base, land, ctypes.addressof(self._leaf_srcs), ctypes.addressof(self._leaf_offs),
+                                 ctypes.addressof(self._leaf_sizes), len(self._batch_layout), self._copy_threads,
+                                 cs.cuda_stream)
+            del keep
             ev = torch.cuda.Event()
-            ev.record()
+            ev.record(cs)
             self._pinned_ev[i] = ev
+            main.wait_event(ev)
+            self.raw_flat.copy_(land, non_blocking=True)
+            free = torch.cuda.Event()
+            free.record(main)
+            self._landing_free[i] = free
         return sum(n for *_, n in self._batch_layout)
 
     @staticmethod
@@ -854,22 +933,6 @@ class UpdateEngine:
         views["_flat"] = flat
         return views
 
-    def h2d_async(self, pinned, slot, copy_stream):
-        """Enqueue the H2D copy of one batch into landing buffer `slot` on `copy_stream`; returns (event, bytes)."""
-        if self._landing is None:
-            self._landing = [torch.empty_like(self.raw_flat) for _ in range(2)]
-        src = pinned["_flat"]
-        with torch.cuda.stream(copy_stream):
-            self._landing[slot].copy_(src, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return ev, sum(n for *_, n in self._batch_layout)
-
-    def adopt(self, slot, event):
-        """Make landing buffer `slot` the current batch (one device-to-device copy on the current stream)."""
-        torch.cuda.current_stream().wait_event(event)
-        self.raw_flat.copy_(self._landing[slot], non_blocking=True)
-
     def to_device_batch(self, pinned):
         """A batch resident in HBM (for set_batch_device)."""
         return {"_flat": pinned["_flat"].to(self.device)}
@@ -892,6 +955,7 @@ class UpdateEngine:
     # ------------------------------------------------------------------ readback
     def read_scalars(self, updates: int, sync=True):
         """One device->host copy of everything update_parameters() logs (vs ~11 .item() syncs, sac.py:140-203)."""
+        self.flush_scalars()
         if self.scalars_host is not None:
             with torch.cuda.device(self.device):
                 self.scalars_host.copy_(self.scalars, non_blocking=True)
@@ -900,6 +964,9 @@ class UpdateEngine:
             s = self.scalars_host.numpy().astype(np.float64)
         else:
             s = self.scalars.cpu().numpy().astype(np.float64)
+        return self._scalars_dict(s, updates)
+
+    def _scalars_dict(self, s, updates):
         hp = self.hp
         pre = hp.algo
         A = self.spec.action_dim
@@ -921,8 +988,40 @@ class UpdateEngine:
         self._alpha_before = float(s[9])
         return ret
 
+    def read_scalars_async(self, updates: int):
+        """The same dict, filled in on first access: the device->host copy of the scalars is enqueued behind the update
+        (pinned ring slot + event) and this call returns at once, so the host can sample and stage the NEXT batch while
+        this update runs.  Reading any entry waits for the event.  Pending results resolve in update order (the alpha an
+        update logs is the one the update before it left, sac.py:152); a slot is never reused before its result was
+        resolved."""
+        if self.scalars_host is None:
+            return self.read_scalars(updates)
+        if self._scalar_ring is None:
+            self._scalar_ring = [torch.zeros(NUM_SCALARS, dtype=torch.float32).pin_memory() for _ in range(SCALAR_RING)]
+            self._scalar_pending = []
+            self._scalar_seq = 0
+        while len(self._scalar_pending) >= SCALAR_RING:
+            self._scalar_pending[0]._resolve()
+        slot = self._scalar_ring[self._scalar_seq % SCALAR_RING]
+        self._scalar_seq += 1
+        with torch.cuda.device(self.device):
+            slot.copy_(self.scalars, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        ret = LazyScalars(self, slot, ev, updates)
+        self._scalar_pending.append(ret)
+        return ret
+
+    def flush_scalars(self):
+        """Resolve every pending asynchronous result (keeps `_alpha_before` and the ring in update order)."""
+        while self._scalar_pending:
+            self._scalar_pending[0]._resolve()
+
+    _scalar_ring = None
+    _scalar_pending = ()
     _alpha_before = 0.0
 
     def prime_alpha(self):
         """host copy of the cached alpha (the value update N logs is the one cached BEFORE update N, sac.py:152)."""
+        self.flush_scalars()
         self._alpha_before = float(self.alpha_dev.item())

@@ -338,3 +338,95 @@ def test_rollout_path_bf16_cached_weights_and_fused_inference_aug():
     assert torch.equal(g_agent(obs, mode="eval"), agent2(obs, mode="eval"))  # replay sees the updated weights
     s1, s2 = g_agent(obs, mode="explore"), g_agent(obs, mode="explore")
     assert not torch.equal(s1, s2)  # the Philox counter advances inside the graph
+
+
+def test_lazy_scalars_is_a_dict_that_resolves_on_access_in_update_order():
+    """engine.LazyScalars (what update_parameters returns): resolved on first access, earlier updates first."""
+    from pointcloud_rl_b200.engine import LazyScalars
+
+    order = []
+
+    class Ev:
+        def __init__(self, i):
+            self.i = i
+
+        def synchronize(self):
+            order.append(self.i)
+
+        def query(self):
+            return True
+
+    class Slot:
+        def __init__(self, v):
+            self.v = np.array([v], np.float32)
+
+        def numpy(self):
+            return self.v
+
+    class Eng:
+        def __init__(self):
+            self._scalar_pending = []
+
+        def _scalars_dict(self, s, updates):
+            return {"loss": float(s[0]), "updates": updates}
+
+    eng = Eng()
+    rets = [LazyScalars(eng, Slot(float(i)), Ev(i), i) for i in range(4)]
+    eng._scalar_pending.extend(rets)
+    assert order == []
+    assert rets[2]["loss"] == 2.0 and order == [0, 1, 2] and eng._scalar_pending == [rets[3]]
+    assert isinstance(rets[3], dict) and dict(rets[3]) == {"loss": 3.0, "updates": 3} and order == [0, 1, 2, 3]
+    assert json.loads(json.dumps(rets[0])) == {"loss": 0.0, "updates": 0}
+    merged = {}
+    merged.update(rets[1])
+    assert merged == {"loss": 1.0, "updates": 1} and len(rets[1]) == 2 and "loss" in rets[1]
+    assert sorted(rets[0].items()) == [("loss", 0.0), ("updates", 0)] and order == [0, 1, 2, 3]
+
+
+@pytest.mark.gpu
+def test_pipelined_updates_equal_synchronous_updates():
+    """update_parameters stages batch i+1 (copy stream + landing buffer) and defers the scalar read-back while update i
+    runs: a loop that reads every result late must produce the scalars, weights and alpha of a loop that reads each result
+    at once (to run-to-run reproducibility: the gradient-norm and weight-gradient sums are float atomics, so two identical
+    synchronous runs already differ in the last bits)."""
+    from oracle import pointnet_sac_oracle as O
+    from pointcloud_rl_b200.data import DictArray
+
+    B, N, A, S = 6, 96, 5, 13
+    obs_shape = {"xyz": [3, N], "rgb": [3, N], "seg": [1, N], "agent": S}
+    batches = [O.synthetic_batch(seed=40 + i, B=B, N=N, A=A, n_seg=1, n_pos=0, state_dim=S) for i in range(5)]
+
+    class Memory:
+        def __init__(self):
+            self.i = 0
+
+        def sample(self, n):
+            b = batches[self.i % len(batches)]
+            self.i += 1
+            return DictArray(b)
+
+    results = {}
+    for mode in ("sync", "late"):
+        torch.manual_seed(3)
+        agent = make_agent("mfrl/drq/maniskill/pn_jitter.py", obs_shape, A, hidden=64, batch_size=B, precision="fp32",
+                           seed=11).to("cuda")
+        mem, rets = Memory(), []
+        for u in range(1, 11):
+            r = agent.update_parameters(mem, u)
+            if mode == "sync":
+                r = dict(r)
+            rets.append(r)
+        if mode == "late":
+            assert len(agent.engine._scalar_pending) == 8  # the ring resolved the two oldest results to reuse their slots
+        alpha = agent.alpha
+        assert not agent.engine._scalar_pending
+        results[mode] = ([dict(r) for r in rets], agent.engine.params.clone(), alpha)
+    (rs, ps, a_s), (rl, pl, a_l) = results["sync"], results["late"]
+    for u, (a, b) in enumerate(zip(rs, rl)):
+        assert a.keys() == b.keys()
+        for k in a:
+            # last-bit differences grow along the trajectory; an update that saw the wrong batch is off by O(1)
+            tol = 1e-3 if u < 6 else 5e-2
+            assert abs(a[k] - b[k]) <= tol * max(1.0, abs(a[k])), (u + 1, k, a[k], b[k])
+    assert abs(a_s - a_l) <= 1e-4
+    assert rs[-1]["drq/alpha"] != rs[0]["drq/alpha"]

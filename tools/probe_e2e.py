@@ -20,7 +20,15 @@ def timeit(fn, n=50):
     for i in range(n): fn(i)
     torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e3
 
-print("full update_parameters            ms:", timeit(lambda i: agent.update_parameters(mem, i + 1)))
+print("update_parameters, result read at once   ms:", timeit(lambda i: dict(agent.update_parameters(mem, i + 1))))
+prev = [None]
+def late(i):
+    cur = agent.update_parameters(mem, i + 1)
+    if prev[0] is not None:
+        prev[0]["drq/critic_loss"]
+    prev[0] = cur
+print("update_parameters, result read a step late ms:", timeit(late))
+agent.engine.flush_scalars()
 print("memory.sample + unwrap            ms:", timeit(lambda i: unwrap(mem.sample(256))))
 b = unwrap(mem.sample(256))
 print("upload_batch (stage + H2D enqueue) ms:", timeit(lambda i: eng.upload_batch(b)))
@@ -32,4 +40,4 @@ print("  H2D of the pinned buffer only   ms:", timeit(lambda i: eng.raw_flat.cop
 print("update_graphed only               ms:", timeit(lambda i: eng.update_graphed(i + 1)))
 print("update_graphed + read_scalars     ms:", timeit(lambda i: (eng.update_graphed(i + 1), eng.read_scalars(i + 1))))
 print("upload + update + scalars         ms:", timeit(lambda i: (eng.upload_batch(b), eng.update_graphed(i + 1), eng.read_scalars(i + 1))))
-print("threads in the staging pool:", eng._copy_pool._max_workers, " cpu_count:", os.cpu_count(), " torch threads:", torch.get_num_threads())
+print("staging memcpy threads:", eng._copy_threads, " cpu_count:", os.cpu_count(), " torch threads:", torch.get_num_threads())
