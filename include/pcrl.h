@@ -304,6 +304,22 @@ int pcrl_adam_step_part(float* p, const float* g, float* m, float* v, int64_t n,
                         float* target, int64_t poly_begin, int64_t poly_end, float tau, void* stream);
 int pcrl_polyak(float* target, const float* source, int64_t n, float tau, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Gradient all-reduce over NVLink peer memory (replaces DistributedDataParallel's NCCL buckets, module_utils.py:322-349,
+ * for the ranks of one node).  In-place SUM of elements [off, off + n) of a SYMMETRIC fp32 buffer: every rank holds a
+ * buffer of the same layout and bufs_dev[r] (a DEVICE array of `world` addresses) is rank r's buffer as mapped into THIS
+ * process (torch.distributed._symmetric_memory / cudaIpcOpenMemHandle); flags_dev[r] likewise addresses rank r's flag
+ * block (pcrl_p2p_flag_bytes() bytes, zero-initialised once, symmetric too).  state_dev: pcrl_p2p_state_bytes() bytes
+ * of LOCAL zero-initialised device memory (per-channel call counters).  channel < PCRL_P2P_CHANNELS: reductions that can
+ * be in flight at the same time (different streams) must use different channels; every rank must issue the same
+ * sequence of calls per channel.  One kernel, stream-ordered, CUDA-graph-capturable; the result is bit-identical on
+ * all ranks (each slice is summed once, in rank order, and broadcast).  max_ctas: 0 = default (32). */
+#define PCRL_P2P_CHANNELS 16
+int64_t pcrl_p2p_flag_bytes(void);
+int64_t pcrl_p2p_state_bytes(void);
+int pcrl_p2p_allreduce(const uint64_t* bufs_dev, const uint64_t* flags_dev, int rank, int world, int64_t off, int64_t n,
+                       int channel, int32_t* state_dev, int max_ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,11 +6,78 @@ actor MLP + d log_alpha after the actor backward) and folds 1/world into the fus
 Deliberate deviation: log_alpha's gradient is reduced too, so alpha stays identical on every rank (the
 reference leaves it un-synced, sac.py:83 + module_utils.py:338-343).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
+from ._lib import stream_ptr
 
-def attach(engine, group=None):
+
+class _EventHandle:
+    """What `allreduce(..., async_op=True)` returns on the peer-memory path: `wait()` makes the current stream wait for
+    the reduction kernel (an event dependency -- also inside CUDA-graph capture), like a c10d work handle does."""
+
+    def __init__(self, event):
+        self.event = event
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.event)
+
+
+class PeerAllReduce:
+    """In-place SUM all-reduce of ranges of the engine's flat gradient buffer through NVLink peer memory
+    (`pcrl_p2p_allreduce`, csrc/p2p.cu): the gradient buffer is re-allocated as symmetric memory (same layout on every
+    rank of the node, mapped into every peer), one kernel per reduction, bit-identical result on all ranks."""
+
+    def __init__(self, engine, group):
+        import torch.distributed._symmetric_memory as symm
+
+        if engine._graphs:
+            raise RuntimeError("the gradient buffer cannot move once update graphs were captured")
+        L, dev = engine.L, engine.device
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        name = group.group_name
+        grads = symm.empty(engine.grads.numel(), dtype=torch.float32, device=dev)
+        self.h_grads = symm.rendezvous(grads, name)
+        flags = symm.empty(int(L.p2p_flag_bytes()) // 4, dtype=torch.int32, device=dev)
+        self.h_flags = symm.rendezvous(flags, name)
+        grads.zero_()
+        flags.zero_()
+        torch.cuda.synchronize(dev)
+        self.h_flags.barrier()  # nobody signals into a flag block that is not zeroed yet
+        self.grads, self.flags = grads, flags
+        self.bufs_dev = torch.tensor([int(p) for p in self.h_grads.buffer_ptrs], dtype=torch.int64, device=dev)
+        self.flags_dev = torch.tensor([int(p) for p in self.h_flags.buffer_ptrs], dtype=torch.int64, device=dev)
+        self.state = torch.zeros(int(L.p2p_state_bytes()) // 4, dtype=torch.int32, device=dev)
+        self.channels = {}
+        self.L = L
+        engine.rebind_grads(grads)
+
+    def __call__(self, flat_grad, async_op=False):
+        if flat_grad.untyped_storage().data_ptr() != self.grads.untyped_storage().data_ptr() or not flat_grad.is_contiguous():
+            raise RuntimeError("peer-memory all-reduce: not a contiguous range of the engine's gradient buffer")
+        key = (flat_grad.storage_offset(), flat_grad.numel())
+        ch = self.channels.setdefault(key, len(self.channels))  # one channel per call site, same order on every rank
+        self.L.p2p_allreduce(self.bufs_dev, self.flags_dev, self.rank, self.world, key[0], key[1], ch, self.state, 0,
+                             stream_ptr())
+        if not async_op:
+            return None
+        ev = torch.cuda.Event()
+        ev.record()
+        return _EventHandle(ev)
+
+    def check(self):
+        """Raises if a reduction gave up waiting for a peer (state[channel][2] != 0)."""
+        err = self.state.view(-1, 4)[:, 2].cpu()
+        if int(err.abs().sum()):
+            raise RuntimeError(f"peer-memory all-reduce timed out waiting for a peer (per channel: {err.tolist()})")
+
+
+def attach(engine, group=None, peer_memory=None):
+    """Installs the gradient all-reduce.  peer_memory: True = NVLink peer-memory kernel (all ranks on one node),
+    False = NCCL, None = peer memory when it can be set up (and PCRL_P2P_ALLREDUCE != 0), else NCCL.  The choice is
+    agreed between the ranks, so a rank whose setup fails takes everybody to NCCL."""
     group = group if group is not None else dist.group.WORLD
     world = dist.get_world_size(group)
     engine.world_size = world
@@ -21,6 +88,27 @@ def attach(engine, group=None):
         return dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
     engine.allreduce = allreduce if world > 1 else None
+    engine.allreduce_kind = "nccl" if world > 1 else None
+    device = getattr(engine, "device", None)
+    if world == 1 or device is None or device.type != "cuda" or dist.get_backend(group) != "nccl":
+        return engine
+    if peer_memory is None:
+        peer_memory = os.environ.get("PCRL_P2P_ALLREDUCE", "1") != "0"
+    want = bool(peer_memory) and world <= 16 and not engine._graphs
+    ok = torch.tensor([1 if want else 0], device=engine.device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if int(ok.item()):
+        p2p, err = None, None
+        try:
+            p2p = PeerAllReduce(engine, group)
+        except Exception as e:  # noqa: BLE001 -- symmetric memory unavailable (ranks on several nodes, no P2P, ...)
+            err = e
+        ok = torch.tensor([0 if p2p is None else 1], device=engine.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()):
+            engine.allreduce, engine.allreduce_kind, engine._p2p = p2p, "peer_memory", p2p
+        elif peer_memory is True and os.environ.get("PCRL_P2P_ALLREDUCE") == "require":
+            raise RuntimeError(f"peer-memory all-reduce requested but unavailable: {err}")
     return engine
 
 

@@ -245,6 +245,17 @@ class UpdateEngine:
         self.allreduce = None  # set by dist.attach(): callable(flat_grad_view)
         self._alloc_workspace(fwd_chunk_clouds)
 
+    def rebind_grads(self, new_grads):
+        """Move the flat gradient buffer (dist.PeerAllReduce re-allocates it as symmetric memory).  Only before the first
+        graph capture: captured kernels hold the old addresses."""
+        if self._graphs:
+            raise RuntimeError("rebind_grads after graph capture")
+        assert new_grads.numel() == self.grads.numel() and new_grads.dtype == self.grads.dtype
+        new_grads.copy_(self.grads)
+        self.grads = new_grads
+        self.g = self.layout.views(self.grads)
+        self.w["dlog_alpha"] = self.g["log_alpha"]
+
     # ------------------------------------------------------------------ buffers
     def _alloc_workspace(self, fwd_chunk_clouds):
         sp, B, R, dev = self.spec, self.B, self.R, self.device

@@ -56,7 +56,9 @@ def main():
         part.load_params(init)
     else:  # other ranks start from garbage: broadcast_state must bring rank 0's weights over
         part.load_params({k: torch.randn_like(v) for k, v in init.items()})
-    attach(part)
+    reduce_kind = sys.argv[3] if len(sys.argv) > 3 else "nccl"
+    attach(part, peer_memory=(reduce_kind == "peer_memory"))
+    assert part.allreduce_kind == reduce_kind, (part.allreduce_kind, reduce_kind)
     broadcast_state(part)
     part.upload_batch(shard(g["batch"], rank, world))
     for u in range(1, m["n_updates"] + 1):
@@ -99,7 +101,10 @@ def main():
     flag = torch.tensor([int(ok)], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("NCCL_2RANK", "PASS" if flag.item() == 1 else "FAIL", precision, "graph" if use_graph else "eager", flush=True)
+        print("NCCL_2RANK", "PASS" if flag.item() == 1 else "FAIL", precision, "graph" if use_graph else "eager",
+              part.allreduce_kind, flush=True)
+    if getattr(part, "_p2p", None) is not None:
+        part._p2p.check()
     # teardown order that does not hang: captured graphs hold NCCL kernels, so they go before the communicator
     part.close()
     whole.close()
