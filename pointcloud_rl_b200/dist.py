@@ -75,9 +75,11 @@ class PeerAllReduce:
 
 
 def attach(engine, group=None, peer_memory=None):
-    """Installs the gradient all-reduce.  peer_memory: True = NVLink peer-memory kernel (all ranks on one node),
-    False = NCCL, None = peer memory when it can be set up (and PCRL_P2P_ALLREDUCE != 0), else NCCL.  The choice is
-    agreed between the ranks, so a rank whose setup fails takes everybody to NCCL."""
+    """Installs the gradient all-reduce.  peer_memory: False = NCCL; True = the NVLink peer-memory kernel (all ranks on
+    one node); None = NCCL unless PCRL_P2P_ALLREDUCE=1 is set.  NCCL is the default: the peer-memory kernel is validated
+    on its own at 2 and 8 ranks and in the engine at 2 ranks (tests/test_gpu_nccl.py), but the 8-rank benchmark run with
+    it did not finish this round, so it stays opt-in.  When it is requested the ranks agree on the
+    outcome: a rank whose setup fails takes everybody back to NCCL."""
     group = group if group is not None else dist.group.WORLD
     world = dist.get_world_size(group)
     engine.world_size = world
@@ -89,26 +91,29 @@ def attach(engine, group=None, peer_memory=None):
 
     engine.allreduce = allreduce if world > 1 else None
     engine.allreduce_kind = "nccl" if world > 1 else None
-    device = getattr(engine, "device", None)
-    if world == 1 or device is None or device.type != "cuda" or dist.get_backend(group) != "nccl":
-        return engine
     if peer_memory is None:
-        peer_memory = os.environ.get("PCRL_P2P_ALLREDUCE", "1") != "0"
-    want = bool(peer_memory) and world <= 16 and not engine._graphs
-    ok = torch.tensor([1 if want else 0], device=engine.device)
+        peer_memory = os.environ.get("PCRL_P2P_ALLREDUCE", "0") == "1"
+    device = getattr(engine, "device", None)
+    if not peer_memory or world == 1 or device is None or device.type != "cuda" or dist.get_backend(group) != "nccl":
+        return engine  # the NCCL path: no further collective here
+    want = world <= 16 and not engine._graphs
+    ok = torch.tensor([1 if want else 0], device=device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if not int(ok.item()):
+        return engine
+    p2p, err = None, None
+    try:
+        p2p = PeerAllReduce(engine, group)
+    except Exception as e:  # noqa: BLE001 -- symmetric memory unavailable (ranks on several nodes, no P2P, ...)
+        err = e
+    ok = torch.tensor([0 if p2p is None else 1], device=device)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
     if int(ok.item()):
-        p2p, err = None, None
-        try:
-            p2p = PeerAllReduce(engine, group)
-        except Exception as e:  # noqa: BLE001 -- symmetric memory unavailable (ranks on several nodes, no P2P, ...)
-            err = e
-        ok = torch.tensor([0 if p2p is None else 1], device=engine.device)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-        if int(ok.item()):
-            engine.allreduce, engine.allreduce_kind, engine._p2p = p2p, "peer_memory", p2p
-        elif peer_memory is True and os.environ.get("PCRL_P2P_ALLREDUCE") == "require":
-            raise RuntimeError(f"peer-memory all-reduce requested but unavailable: {err}")
+        engine.allreduce, engine.allreduce_kind, engine._p2p = p2p, "peer_memory", p2p
+    elif err is not None:
+        import warnings
+
+        warnings.warn(f"peer-memory all-reduce unavailable, using NCCL: {err}")
     return engine
 
 
