@@ -51,3 +51,23 @@ def test_sass_uses_blackwell_tensor_and_tma_paths():
     sass = subprocess.run([cuobjdump, "-sass", LIB_PATH], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass and "LDTM" in sass and "UBLKCP" in sass
     assert "sm_100a" in subprocess.run([cuobjdump, "-lelf", LIB_PATH], capture_output=True, text=True).stdout
+
+
+def test_host_side_helpers_run_without_a_gpu():
+    """pcrl_host_memcpy_mt is pure host code (the staging half of the batch upload): exact bytes for every size / thread
+    count, including the single-threaded small-copy path; the size queries of the peer-memory all-reduce are host-only."""
+    import numpy as np
+
+    L = lib()
+    rng = np.random.default_rng(0)
+    for nbytes in (0, 1, 63, 4096, (256 << 10) - 1, 256 << 10, (1 << 20) + 13, 5_000_003):
+        src = rng.integers(0, 256, size=nbytes + 64, dtype=np.uint8)
+        for threads in (1, 2, 4, 7):
+            dst = np.full(nbytes + 64, 0xA5, dtype=np.uint8)
+            rc = L.cdll.pcrl_host_memcpy_mt(ctypes.c_void_p(dst.ctypes.data + 3), ctypes.c_void_p(src.ctypes.data + 5),
+                                            ctypes.c_int64(nbytes), ctypes.c_int(threads))
+            assert rc == 0
+            assert np.array_equal(dst[3:3 + nbytes], src[5:5 + nbytes]), (nbytes, threads)
+            assert (dst[:3] == 0xA5).all() and (dst[3 + nbytes:] == 0xA5).all(), (nbytes, threads)
+    assert L.cdll.pcrl_host_memcpy_mt(None, None, ctypes.c_int64(16), ctypes.c_int(2)) != 0  # NULL with bytes: rejected
+    assert L.p2p_flag_bytes() == 16 * 2 * 16 * 4 and L.p2p_state_bytes() == 16 * 4 * 4
