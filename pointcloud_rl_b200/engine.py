@@ -9,6 +9,8 @@ Redundant work the reference does is removed without changing the maths: the 6 P
 update collapse to the 3 distinct ones (next_obs, obs with grad, first-aug obs with post-step weights),
 and the two Q heads' feature gradients are summed before the single PointNet backward.
 """
+import ctypes
+import os
 from dataclasses import dataclass, field
 from typing import Dict, Optional, Tuple
 
@@ -16,9 +18,6 @@ import numpy as np
 import torch
 
 from ._lib import lib, stream_ptr
-
-import ctypes
-import os
 
 _NO_FORK = os.environ.get("PCRL_NO_FORK", "")
 S_NAMES = [

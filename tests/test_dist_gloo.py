@@ -32,7 +32,11 @@ def _worker(rank, world, port, out):
     from pointcloud_rl_b200.dist import attach, broadcast_params, broadcast_state
 
     eng = attach(_FakeEngine())
-    assert eng.world_size == world and eng.allreduce is not None
+    assert eng.world_size == world and eng.allreduce is not None and eng.allreduce_kind == "nccl"
+    # the NVLink peer-memory kernel needs CUDA + NCCL: asking for it on a CPU / gloo group quietly keeps the plain
+    # all-reduce (and must not issue a collective the other rank does not)
+    eng2 = attach(_FakeEngine(), peer_memory=(rank == 0))
+    assert eng2.allreduce_kind == "nccl" and eng2.allreduce is not None
     # each rank's gradient is a mean over its own equal-sized shard; sum * (1/world) == global mean
     torch.manual_seed(0)
     per_sample = torch.randn(world * 4, 6)
