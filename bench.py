@@ -679,7 +679,18 @@ def main():
     ap.add_argument("--global-batch", type=int, default=0,
                     help="strong scaling (SURVEY.md section 8d row 4): split this global minibatch over the ranks "
                          "(e.g. 256 or 2048); default 0 = weak scaling, the workload's batch on every rank")
+    ap.add_argument("--allreduce", default="nccl", choices=["nccl", "peer_memory"],
+                    help="N > 1: gradient all-reduce through NCCL (default) or the NVLink peer-memory kernel "
+                         "(pcrl_p2p_allreduce; experimental, DESIGN.md section 7)")
     args = ap.parse_args()
+    # watchdog: a rank that is still here after PCRL_BENCH_WATCHDOG seconds (default 25 min; a default run needs ~2) dumps
+    # every thread's Python stack and exits instead of hanging the box until somebody else's limit kills it
+    watchdog = float(os.environ.get("PCRL_BENCH_WATCHDOG", "1500"))
+    if watchdog > 0:
+        import faulthandler
+
+        faulthandler.dump_traceback_later(watchdog, exit=True)
+    os.environ["PCRL_P2P_ALLREDUCE"] = "1" if args.allreduce == "peer_memory" else "0"
     w = dict(WORKLOADS[args.workload])
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
