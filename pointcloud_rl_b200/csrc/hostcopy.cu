@@ -2,6 +2,8 @@
 // reads).  A single thread moves ~18 GB/s, so the 10 MB ManiSkill batch costs 0.56 ms of the 1.9 ms end-to-end update;
 // a few threads bring it to the PCIe copy's own 0.19 ms.  A small persistent pool (created on first use): python-level
 // thread pools pay ~25 us per task for these ~1 MB pieces, which eats the gain.
+#include <unistd.h>
+
 #include <atomic>
 #include <condition_variable>
 #include <cstring>
@@ -87,9 +89,20 @@ struct CopyPool {
   }
 };
 
+// One pool per PROCESS: worker threads do not survive fork() (the reference forks rollout / evaluation workers), so a
+// child that stages a batch gets a fresh pool instead of waiting for threads that only exist in its parent.  The parent's
+// pool object is deliberately leaked in the child (its mutex / condition variables may be in any state).
 CopyPool& pool() {
-  static CopyPool p;
-  return p;
+  static std::mutex guard;
+  static CopyPool* p = nullptr;
+  static pid_t owner = 0;
+  std::lock_guard<std::mutex> lk(guard);
+  const pid_t me = getpid();
+  if (!p || owner != me) {
+    p = new CopyPool();
+    owner = me;
+  }
+  return *p;
 }
 
 }  // namespace

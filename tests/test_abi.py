@@ -71,3 +71,32 @@ def test_host_side_helpers_run_without_a_gpu():
             assert (dst[:3] == 0xA5).all() and (dst[3 + nbytes:] == 0xA5).all(), (nbytes, threads)
     assert L.cdll.pcrl_host_memcpy_mt(None, None, ctypes.c_int64(16), ctypes.c_int(2)) != 0  # NULL with bytes: rejected
     assert L.p2p_flag_bytes() == 16 * 2 * 16 * 4 and L.p2p_state_bytes() == 16 * 4 * 4
+
+
+def test_host_memcpy_pool_survives_fork():
+    """The staging pool's worker threads do not exist in a forked child (the reference forks rollout workers): the child
+    must get its own pool instead of waiting for the parent's threads."""
+    import numpy as np
+
+    L = lib()
+    n = 2 << 20
+    src = np.arange(n, dtype=np.uint8)
+    dst = np.zeros(n, dtype=np.uint8)
+    assert L.cdll.pcrl_host_memcpy_mt(ctypes.c_void_p(dst.ctypes.data), ctypes.c_void_p(src.ctypes.data), ctypes.c_int64(n),
+                                      ctypes.c_int(4)) == 0  # the parent's pool exists now
+    pid = os.fork()
+    if pid == 0:
+        code = 1
+        try:
+            import signal
+
+            signal.alarm(20)  # a child that waits for threads it does not have is killed, not left hanging
+            d2 = np.zeros(n, dtype=np.uint8)
+            rc = L.cdll.pcrl_host_memcpy_mt(ctypes.c_void_p(d2.ctypes.data), ctypes.c_void_p(src.ctypes.data),
+                                            ctypes.c_int64(n), ctypes.c_int(4))
+            code = 0 if rc == 0 and np.array_equal(d2, src) else 2
+        finally:
+            os._exit(code)
+    _, status = os.waitpid(pid, 0)
+    assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0, status
+    assert np.array_equal(dst, src)
